@@ -1,0 +1,400 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path of GNNAdvisor on B200: neighbour-group SpMM aggregation.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        (N > 1, one rank per GPU)
+
+Workload (BASELINE.json: "aggregation throughput (edges*hidden_dim/sec) on Reddit at D=64"):
+a Reddit look-alike graph (232 965 nodes, 114 615 892 directed edges, symmetric, skewed; there are
+no dataset files offline -- SURVEY.md 8d) and ONE step = one GCN-normalised aggregation
+out = Ahat @ T of a [N, 64] fp32 feature matrix, i.e. the kernel that replaces
+spmm_forward_cuda_kernel / spmm_backward_cuda_kernel (GNNAdvisor_kernel.cu:324-415, 478-552).
+
+One JSON line on stdout (rank 0):
+  value        edges*D per second, whole job, inputs resident in HBM, CUDA-event timed
+  e2e          the same metric through the public API with HOST (pinned) feature buffers:
+               H2D of the features + aggregation + D2H of the result inside the timed region
+  roofline     algorithmic bytes / measured step time vs the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline the CPU oracle (OpenMP port of the reference algorithm) on this box's host cores
+  extras       gcn_epoch_ms (2-layer GCN fwd+bwd+Adam), bf16 gather variant, the reference's own CUDA
+               kernels recompiled for sm_100a on the same tensors (ref_gpu), clocks.
+--impl reference times the CPU port of the reference algorithm (the reference has no CPU path of its
+own) on all host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PEAK_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit", choices=["reddit", "ogbn-products", "amazon0505", "cora", "citeseer"])
+    ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only; reported in config)")
+    ap.add_argument("--part-size", type=int, default=32)
+    ap.add_argument("--dim-worker", type=int, default=32)
+    ap.add_argument("--warp-per-block", type=int, default=8)
+    ap.add_argument("--no-extras", action="store_true", help="skip epoch / bf16 / ref_gpu / cpu_baseline legs")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy, burst)"
+        except Exception:
+            pass
+    return PEAK_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def alg_bytes(E, N, D, P, sx=4, sy=4, gcn=True):
+    """E*(D*sx + 4 [+4 GCN degree gather]) + N*(D*sy + 8) + part table (2P+1)*4."""
+    return E * (D * sx + 4 + (4 if gcn else 0)) + N * (D * sy + 8) + (2 * P + 1) * 4
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled every 20 ms with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.t = [], set(), False, None
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # noqa: BLE001
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.t:
+            self.t.join()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def timed(fn, steps, warmup, barrier=None):
+    """W warm-up steps, then exactly K steps between two CUDA events on the current stream, bracketed
+    by (barrier +) synchronize on both sides.  Returns total milliseconds."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return t0.elapsed_time(t1)
+
+
+def build_workload(args, device):
+    from gnnadvisor_osdi21_b200 import graph, ops
+    gr = graph.lookalike(args.workload, device=device, scale=args.scale)
+    rp, ci = gr["row_ptr"], gr["col_idx"]
+    pp, pn = ops.build_part(args.part_size, rp)          # device build_part
+    deg = ops.degrees_from_row_ptr(rp)
+    gen = torch.Generator(device=device).manual_seed(20212)
+    X = torch.randn(gr["num_nodes"], args.dim, device=device, generator=gen)
+    return gr, rp, ci, pp, pn, deg, X
+
+
+def config_of(args, N, E, P, extra=None):
+    c = {"workload": "%s look-alike GCN aggregation (synthetic rmat, symmetric): N=%d E=%d D=%d fp32" % (args.workload, N, E, args.dim),
+         "num_nodes": N, "num_edges": E, "dim": args.dim, "num_parts": P,
+         "partSize": args.part_size, "dimWorker": args.dim_worker, "warpPerBlock": args.warp_per_block,
+         "scale": args.scale,
+         "l2": "inputs (col_idx %.0f MB + features %.0f MB + group table %.0f MB) exceed the 126 MB L2; no flush between steps"
+               % (E * 4 / 1e6, N * args.dim * 4 / 1e6, (2 * P + 1) * 4 / 1e6)}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_pass(args, rp, ci, pp, pn, deg, X, seconds):
+    """Time the oracle (OpenMP port of the reference algorithm) on all host cores; bounded by `seconds`."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    rpn, cin, ppn, pnn = rp.cpu().numpy(), ci.cpu().numpy(), pp.cpu().numpy(), pn.cpu().numpy()
+    degn, Xn = deg.cpu().numpy(), X.cpu().numpy()
+    E, D = len(cin), Xn.shape[1]
+    cores = len(os.sched_getaffinity(0))
+    # sample = the first `frac` of the groups (whole nodes), sized from one quick probe
+    probe_groups = min(len(pnn), 200_000)
+    t = time.perf_counter()
+    oracle.aggregate(1, Xn, cin, degn, 1.0, ppn[:probe_groups + 1], pnn[:probe_groups], threads=-1)
+    dt = time.perf_counter() - t
+    per_group = dt / max(probe_groups, 1)
+    groups = int(min(len(pnn), max(probe_groups, seconds / 3 / max(per_group, 1e-12))))
+    while 0 < groups < len(pnn) and pnn[groups] == pnn[groups - 1]:
+        groups += 1
+    edges = int(ppn[groups] - ppn[0]) if groups < len(pnn) else E
+    best = None
+    for _ in range(3):
+        t = time.perf_counter()
+        oracle.aggregate(1, Xn, cin, degn, 1.0, ppn[:groups + 1], pnn[:groups], threads=-1)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return {"value": edges * D / best, "unit": "edge*dim/s", "cores": cores, "kind": "port",
+            "sample": "first %d of %d neighbour-groups (%d of %d edges) of the same graph, D=%d, best of 3, %d OpenMP threads"
+                      % (groups, len(pnn), edges, E, D, oracle.num_threads()),
+            "seconds": best}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+    gr, rp, ci, pp, pn, deg, X = build_workload(args, device) if device.type == "cuda" else _cpu_workload(args)
+    N, E, P = gr["num_nodes"], ci.numel(), pn.numel()
+    vals = []
+    per = max(2.0, min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1)))
+    for i in range(args.warmup + args.steps):
+        r = cpu_pass(args, rp, ci, pp, pn, deg, X, per)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    line = {"impl": "reference", "metric": "aggregation throughput (GCN SpMM), edges*dim/s", "value": v, "unit": "edge*dim/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean([r["seconds"] for r in vals]) * 1e3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(args, N, E, P),
+            "cpu_baseline": dict(vals[-1], value=v),
+            "e2e": {"value": v, "unit": "edge*dim/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def _cpu_workload(args):
+    from gnnadvisor_osdi21_b200 import graph
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    gr = graph.lookalike(args.workload, device="cpu", scale=args.scale)
+    rp, ci = gr["row_ptr"], gr["col_idx"]
+    pp, pn = oracle.build_part(args.part_size, rp.numpy(), exact=True)
+    deg = torch.from_numpy(oracle.degrees(rp.numpy()))
+    X = torch.randn(gr["num_nodes"], args.dim, generator=torch.Generator().manual_seed(20212))
+    return gr, rp, ci, torch.from_numpy(pp), torch.from_numpy(pn), deg, X
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def gcn_aggregate_fn(X, out, rp, ci, deg, pp, pn, args):
+    import ctypes
+    from gnnadvisor_osdi21_b200 import _lib
+    lib = _lib.load()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+    n, d = X.shape
+    a = (p(X), p(out), p(rp), p(ci), p(deg), p(pp), p(pn), n, d, pn.numel(),
+         args.part_size, args.dim_worker, args.warp_per_block)
+
+    def step():
+        _lib.check(lib.gnna_gcn_aggregate_f32(*a, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "gcn_aggregate")
+    return step
+
+
+def run_single(args):
+    from gnnadvisor_osdi21_b200 import _lib, ops
+    device = torch.device("cuda:0")
+    torch.cuda.set_device(device)
+    gr, rp, ci, pp, pn, deg, X = build_workload(args, device)
+    N, E, P, D = gr["num_nodes"], ci.numel(), pn.numel(), args.dim
+    out = torch.empty_like(X)
+    step = gcn_aggregate_fn(X, out, rp, ci, deg, pp, pn, args)
+
+    # ---- device-resident throughput (value) with clocks sampled during the timed region
+    sampler = ClockSampler(0)
+    step(); torch.cuda.synchronize()
+    _lib.launch_count(reset=True)
+    sampler.start()
+    total_ms = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches_all = _lib.launch_count()
+    launches = launches_all * args.steps // (args.steps + args.warmup)
+    ms = total_ms / args.steps
+    value = E * D / (ms * 1e-3)
+
+    # ---- roofline of the aggregation kernel
+    peak, peak_src = peak_gbs()
+    B = alg_bytes(E, N, D, P)
+    achieved = B / (ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("%s_D%d_f32" % (args.workload, D))
+        except Exception:   # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "gnna::aggregate_kernel<float,4,16,1,true>",
+                "alg_bytes_per_launch": B, "peak_source": peak_src,
+                "note": "step = cudaMemsetAsync(out) + one kernel launch, timed together; features (%.0f MB) fit in L2, so "
+                        "achieved may exceed the HBM copy peak -- see traffic (ncu dram bytes per launch)" % (N * D * 4 / 1e6)}
+
+    # ---- end to end through the public API with host buffers
+    # the aggregation-only entry of the C ABI (gnna_gcn_aggregate_f32, the kernel behind
+    # GNNAdvisor.forward/backward) called on features that start and end in pinned HOST memory
+    x_host = X.cpu().pin_memory()
+    out_host = torch.empty_like(x_host).pin_memory()
+    x_dev, o_dev = torch.empty_like(X), torch.empty_like(X)
+    e2e_kernel = gcn_aggregate_fn(x_dev, o_dev, rp, ci, deg, pp, pn, args)
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)
+        e2e_kernel()
+        out_host.copy_(o_dev, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 50))
+    e2e_ms = timed(e2e_step, e2e_steps, max(3, min(args.warmup, 5))) / e2e_steps
+    e2e = {"value": E * D / (e2e_ms * 1e-3), "unit": "edge*dim/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(N * D * 4), "d2h_bytes_per_step": int(N * D * 4),
+           "note": "pinned host features -> H2D -> aggregation -> D2H of the [N,D] result, graph (CSR + group table) resident"}
+
+    line = {"metric": "aggregation throughput (GCN SpMM), edges*dim/s", "value": value, "unit": "edge*dim/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(args, N, E, P), "roofline": roofline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "impl": "ours"}
+
+    if not args.no_extras:
+        extras = {}
+        # bf16 gather variant (extension; halves the gather bytes)
+        try:
+            Xb = X.to(torch.bfloat16)
+            f = lambda: ops.aggregate_bf16(1, Xb, rp, ci, deg, 1.0, pp, pn, args.part_size, args.dim_worker, args.warp_per_block)   # noqa: E731
+            bms = timed(f, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
+            Bb = alg_bytes(E, N, D, P, sx=2)
+            extras["bf16_gather"] = {"ms": bms, "edge_dim_per_s": E * D / (bms * 1e-3), "achieved_GBs": Bb / (bms * 1e-3) / 1e9,
+                                     "frac": Bb / (bms * 1e-3) / 1e9 / peak}
+        except Exception as e:   # noqa: BLE001
+            extras["bf16_gather"] = {"error": str(e)}
+        # 2-layer GCN epoch (forward + backward + Adam), mirrors GNNA_main.py:142-202
+        try:
+            extras["gcn_epoch_ms"] = gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device)
+        except Exception as e:   # noqa: BLE001
+            extras["gcn_epoch_ms"] = {"error": str(e)}
+        # the reference's own CUDA kernels, recompiled for sm_100a, on the same tensors
+        try:
+            extras["ref_gpu"] = ref_gpu(args, X, rp, ci, deg, pp, pn, step, ms)
+        except Exception as e:   # noqa: BLE001
+            extras["ref_gpu"] = {"error": str(e)}
+        line["extras"] = extras
+        try:
+            line["cpu_baseline"] = cpu_pass(args, rp, ci, pp, pn, deg, X, args.cpu_seconds)
+        except Exception as e:   # noqa: BLE001
+            line["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(line))
+
+
+def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device):
+    import torch.nn.functional as F
+    from gnnadvisor_osdi21_b200 import layers
+
+    class Info:
+        pass
+    info = Info()
+    info.row_pointers, info.column_index, info.degrees, info.partPtr, info.part2Node = rp, ci, deg, pp, pn
+    info.partSize, info.dimWorker, info.warpPerBlock = args.part_size, args.dim_worker, args.warp_per_block
+    n = gr["num_nodes"]
+    x = torch.randn(n, gr["in_dim"], device=device)
+    y = torch.ones(n, dtype=torch.long, device=device)
+    c1, c2 = layers.GCNConv(gr["in_dim"], gr["hidden"]).to(device), layers.GCNConv(gr["hidden"], gr["classes"]).to(device)
+    opt = torch.optim.Adam(list(c1.parameters()) + list(c2.parameters()), lr=0.01)
+
+    def train():
+        opt.zero_grad()
+        h = F.relu(c1(x, info))
+        o = F.log_softmax(c2(h, info), dim=1)
+        F.nll_loss(o, y).backward()
+        opt.step()
+    k = max(3, min(args.steps // 5, 20))
+    return {"ms": timed(train, k, 3) / k, "epochs_timed": k,
+            "model": "GCN %d-%d-%d, fwd+bwd+Adam (GNNA_main.py:142-202)" % (gr["in_dim"], gr["hidden"], gr["classes"])}
+
+
+def ref_gpu(args, X, rp, ci, deg, pp, pn, our_step, our_ms):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    ref = build_ref.load_ref()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/GNNAdvisor_ref.so not built"}
+    from gnnadvisor_osdi21_b200 import ops
+    D = X.shape[1]
+    E = ci.numel()
+    W = torch.eye(D, device=X.device)
+    a = (rp, ci, deg, pp, pn, args.part_size, args.dim_worker, args.warp_per_block)
+    k = 5
+    r_sag = timed(lambda: ref.SAG(X, *a), k, 2) / k
+    o_sag = timed(lambda: ops.SAG(X, *a), k, 2) / k
+    r_fwd = timed(lambda: ref.forward(X, W, *a), k, 2) / k
+    o_fwd = timed(lambda: ops.forward(X, W, *a), k, 2) / k
+    yr, yo = ref.forward(X, W, *a)[0], ops.forward(X, W, *a)[0]
+    rel = ((yr - yo).abs().max() / yr.abs().max()).item()
+    return {"what": "reference kernels (GNNAdvisor_kernel.cu) recompiled for sm_100a, same tensors, exact group table",
+            "ref_SAG_ms": r_sag, "ours_SAG_ms": o_sag, "ref_forward_ms": r_fwd, "ours_forward_ms": o_fwd,
+            "speedup_SAG": r_sag / o_sag, "speedup_forward": r_fwd / o_fwd,
+            "ref_edge_dim_per_s": E * D / (r_fwd * 1e-3), "max_abs_diff_over_max": rel}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from gnnadvisor_osdi21_b200 import dist_bench
+        return dist_bench.run(args, sys.modules[__name__])
+    run_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""ctypes binding of libgnna_b200.so (C ABI: include/gnna_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, this raises.  Nothing in this
+package computes an aggregation on the CPU or through torch ops.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libgnna_b200.so")
+
+c_i32p = ctypes.c_void_p
+c_f32p = ctypes.c_void_p
+i64 = ctypes.c_int64
+i32 = ctypes.c_int
+
+
+class LaunchInfo(ctypes.Structure):
+    _fields_ = [("vec_width", i32), ("lanes_per_row", i32), ("chunks_per_lane", i32),
+                ("warps_per_block", i32), ("groups_per_warp", i32), ("grid_x", i64),
+                ("grid_y", i32), ("kernels", i32)]
+
+
+# name -> (restype, argtypes); the single place that mirrors include/gnna_b200.h
+_GRAPH = [c_i32p, c_i32p]                       # row_ptr, col_idx
+_PARTS = [c_i32p, c_i32p]                       # part_ptr, part2node
+_TUNE = [i32, i32, i32, ctypes.c_void_p]        # part_size, dim_worker, warp_per_block, stream
+SIGNATURES = {
+    "gnna_abi_version": (i32, []),
+    "gnna_last_error": (ctypes.c_char_p, []),
+    "gnna_count_parts_host": (i64, [i32, c_i32p, i64]),
+    "gnna_build_part_host": (i32, [i32, c_i32p, i64, c_i32p, c_i32p, i64, i32]),
+    "gnna_build_part_device": (i32, [i32, c_i32p, i64, c_i32p, c_i32p, ctypes.POINTER(i64),
+                                     ctypes.c_void_p, i64, ctypes.c_void_p]),
+    "gnna_build_part_workspace_bytes": (i64, [i64]),
+    "gnna_degrees": (i32, [c_i32p, i64, c_f32p, ctypes.c_void_p]),
+    "gnna_sag_f32": (i32, [c_f32p, c_f32p] + _GRAPH + _PARTS + [i64, i32, i64] + _TUNE),
+    "gnna_gcn_aggregate_f32": (i32, [c_f32p, c_f32p] + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i64] + _TUNE),
+    "gnna_gin_aggregate_f32": (i32, [c_f32p, c_f32p] + _GRAPH + [ctypes.c_float] + _PARTS + [i64, i32, i64] + _TUNE),
+    "gnna_aggregate_bf16": (i32, [i32, ctypes.c_void_p, c_f32p] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
+                            + [i64, i32, i64] + _TUNE),
+    "gnna_forward_f32": (i32, [c_f32p] * 4 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
+    "gnna_backward_f32": (i32, [c_f32p] * 6 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
+    "gnna_forward_gin_f32": (i32, [c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p] + _GRAPH + _PARTS
+                             + [i64, i32, i32, i64] + _TUNE),
+    "gnna_backward_gin_f32": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, c_f32p] + _GRAPH + _PARTS
+                              + [i64, i32, i32, i64] + _TUNE),
+    "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
+    "gnna_launch_count": (i64, [i32]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library; raises if it has not been built (python -m gnnadvisor_osdi21_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libgnna_b200.so is missing (%s). Build it with `python -m gnnadvisor_osdi21_b200.build`; "
+            "there is no CPU or torch fallback for this path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().gnna_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count(reset=False):
+    return int(load().gnna_launch_count(1 if reset else 0))

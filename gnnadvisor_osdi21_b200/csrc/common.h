@@ -1,0 +1,38 @@
+// Shared helpers of libgnna_b200.so (error text, launch counter, argument checks).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/gnna_b200.h"
+
+namespace gnna {
+
+char *error_buffer();                       // thread-local, 512 bytes
+int fail(int code, const char *fmt, ...);   // formats into error_buffer(), returns code
+void count_launch(int n = 1);               // thread-local launch counter
+
+#define GNNA_CUDA_CHECK(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ::gnna::fail(GNNA_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                       \
+    } while (0)
+
+#define GNNA_REQUIRE(cond, ...)                                       \
+    do {                                                              \
+        if (!(cond)) return ::gnna::fail(GNNA_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+enum Mode { MODE_SAG = 0, MODE_GCN = 1, MODE_GIN = 2 };
+
+// One aggregation launch (aggregate.cu).  elem: 4 = fp32, 2 = bf16.
+int aggregate(int mode, int elem_bytes, const void *X, void *out,
+              const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
+              const int32_t *part_ptr, const int32_t *part2node,
+              int64_t num_nodes, int dim, int64_t num_parts,
+              int part_size, int dim_worker, int warp_per_block, cudaStream_t stream);
+
+}  // namespace gnna

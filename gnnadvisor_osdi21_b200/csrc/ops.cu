@@ -1,0 +1,188 @@
+// ops.cu -- C-ABI entry points: error plumbing, the three aggregation calls and the four layer
+// operators (aggregation + the dense products the reference does with torch::mm).
+//
+// Reference host launchers replaced here (GNNAdvisor/GNNConv/GNNAdvisor_kernel.cu):
+//   SAG_cuda :110-184, spmm_forward_cuda :267-322, spmm_backward_cuda :422-476,
+//   spmm_forward_cuda_gin :559-617, spmm_backward_cuda_gin :696-747.
+// The dense products stay library SGEMMs (cuBLAS, fp32, TF32 off) exactly as torch::mm is in the
+// reference; every one of them has min(din, dout) <= 64 at fp32 in the reference's configurations
+// and is bandwidth-bound, so the aggregation kernel is where the time goes.
+#include <cublas_v2.h>
+
+#include <mutex>
+
+#include "common.h"
+
+namespace gnna {
+
+static thread_local char g_err[512];
+static thread_local long long g_launches = 0;
+
+char *error_buffer() { return g_err; }
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+// one cuBLAS handle per device, created on first use
+static std::mutex g_handle_mutex;
+static cublasHandle_t g_handles[64] = {nullptr};
+
+static int get_handle(cublasHandle_t *h)
+{
+    int dev = 0;
+    GNNA_CUDA_CHECK(cudaGetDevice(&dev));
+    GNNA_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_handle_mutex);
+    if (!g_handles[dev]) {
+        cublasStatus_t s = cublasCreate(&g_handles[dev]);
+        if (s != CUBLAS_STATUS_SUCCESS) {
+            g_handles[dev] = nullptr;
+            return fail(GNNA_ERR_CUBLAS, "cublasCreate failed (%d)", (int)s);
+        }
+        cublasSetMathMode(g_handles[dev], CUBLAS_DEFAULT_MATH);    // plain fp32 SGEMM, TF32 stays off (as torch::mm)
+    }
+    *h = g_handles[dev];
+    return GNNA_OK;
+}
+
+// C[m,n] = op(A) * op(B), all row-major.  Row-major C = A*B is column-major C^T = B^T * A^T.
+static int sgemm_rm(cudaStream_t st, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
+                    const float *A, const float *B, float *C)
+{
+    if (m == 0 || n == 0) return GNNA_OK;
+    cublasHandle_t h;
+    int rc = get_handle(&h);
+    if (rc != GNNA_OK) return rc;
+    cublasSetStream(h, st);
+    const float one = 1.f, zero = 0.f;
+    const int64_t lda = ta ? m : k, ldb = tb ? k : n;
+    if (k == 0) {
+        GNNA_CUDA_CHECK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)m * (size_t)n, st));
+        return GNNA_OK;
+    }
+    cublasStatus_t s = cublasSgemm_64(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N,
+                                      n, m, k, &one, B, ldb, A, lda, &zero, C, n);
+    if (s != CUBLAS_STATUS_SUCCESS) return fail(GNNA_ERR_CUBLAS, "cublasSgemm failed (%d)", (int)s);
+    return GNNA_OK;
+}
+
+}  // namespace gnna
+
+using namespace gnna;
+
+extern "C" int gnna_abi_version(void) { return 1; }
+extern "C" const char *gnna_last_error(void) { return error_buffer(); }
+
+extern "C" int64_t gnna_launch_count(int reset)
+{
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+extern "C" int gnna_sag_f32(const float *X, float *out, const int32_t *row_ptr, const int32_t *col_idx,
+                            const int32_t *part_ptr, const int32_t *part2node,
+                            int64_t num_nodes, int dim, int64_t num_parts,
+                            int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    return aggregate(MODE_SAG, 4, X, out, row_ptr, col_idx, nullptr, 1.f, part_ptr, part2node, num_nodes, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream);
+}
+
+extern "C" int gnna_gcn_aggregate_f32(const float *X, float *out, const int32_t *row_ptr, const int32_t *col_idx,
+                                      const float *degrees, const int32_t *part_ptr, const int32_t *part2node,
+                                      int64_t num_nodes, int dim, int64_t num_parts,
+                                      int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    return aggregate(MODE_GCN, 4, X, out, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream);
+}
+
+extern "C" int gnna_gin_aggregate_f32(const float *X, float *out, const int32_t *row_ptr, const int32_t *col_idx,
+                                      float eps, const int32_t *part_ptr, const int32_t *part2node,
+                                      int64_t num_nodes, int dim, int64_t num_parts,
+                                      int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    return aggregate(MODE_GIN, 4, X, out, row_ptr, col_idx, nullptr, eps, part_ptr, part2node, num_nodes, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream);
+}
+
+extern "C" int gnna_aggregate_bf16(int mode, const void *X_bf16, float *out_f32, const int32_t *row_ptr,
+                                   const int32_t *col_idx, const float *degrees, float eps,
+                                   const int32_t *part_ptr, const int32_t *part2node,
+                                   int64_t num_nodes, int dim, int64_t num_parts,
+                                   int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    return aggregate(mode, 2, X_bf16, out_f32, row_ptr, col_idx, degrees, eps, part_ptr, part2node, num_nodes, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream);
+}
+
+#define GNNA_TRY(expr)             \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != GNNA_OK) return _rc; \
+    } while (0)
+
+extern "C" int gnna_forward_f32(const float *X, const float *W, float *T_ws, float *out,
+                                const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                                const int32_t *part_ptr, const int32_t *part2node,
+                                int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(X && W && T_ws && out, "gnna_forward_f32: null pointer");
+    GNNA_TRY(sgemm_rm(st, false, false, num_nodes, dout, din, X, W, T_ws));               // kernel.cu:280
+    return aggregate(MODE_GCN, 4, T_ws, out, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes, dout,
+                     num_parts, part_size, dim_worker, warp_per_block, st);               // kernel.cu:282-313
+}
+
+extern "C" int gnna_backward_f32(const float *d_out, const float *X, const float *W, float *G_ws,
+                                 float *d_input, float *d_weight,
+                                 const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                                 const int32_t *part_ptr, const int32_t *part2node,
+                                 int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                 int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(d_out && X && W && G_ws && d_weight, "gnna_backward_f32: null pointer");
+    GNNA_TRY(aggregate(MODE_GCN, 4, d_out, G_ws, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes, dout,
+                       num_parts, part_size, dim_worker, warp_per_block, st));            // kernel.cu:436-463
+    if (d_input) GNNA_TRY(sgemm_rm(st, false, true, num_nodes, din, dout, G_ws, W, d_input));   // :472
+    return sgemm_rm(st, true, false, din, dout, num_nodes, X, G_ws, d_weight);            // :473
+}
+
+extern "C" int gnna_forward_gin_f32(const float *X, const float *W, float eps, float *out, float *x_agg,
+                                    const int32_t *row_ptr, const int32_t *col_idx,
+                                    const int32_t *part_ptr, const int32_t *part2node,
+                                    int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                    int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(X && W && out && x_agg, "gnna_forward_gin_f32: null pointer");
+    GNNA_TRY(aggregate(MODE_GIN, 4, X, x_agg, row_ptr, col_idx, nullptr, eps, part_ptr, part2node, num_nodes, din,
+                       num_parts, part_size, dim_worker, warp_per_block, st));            // kernel.cu:572-603
+    return sgemm_rm(st, false, false, num_nodes, dout, din, x_agg, W, out);               // :605
+}
+
+extern "C" int gnna_backward_gin_f32(const float *d_out, const float *x_agg, const float *W, float eps,
+                                     float *Pm_ws, float *d_input, float *d_weight,
+                                     const int32_t *row_ptr, const int32_t *col_idx,
+                                     const int32_t *part_ptr, const int32_t *part2node,
+                                     int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                     int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(d_out && x_agg && W && Pm_ws && d_input && d_weight, "gnna_backward_gin_f32: null pointer");
+    GNNA_TRY(sgemm_rm(st, true, false, din, dout, num_nodes, x_agg, d_out, d_weight));    // kernel.cu:710
+    GNNA_TRY(sgemm_rm(st, false, true, num_nodes, din, dout, d_out, W, Pm_ws));           // :711
+    return aggregate(MODE_GIN, 4, Pm_ws, d_input, row_ptr, col_idx, nullptr, eps, part_ptr, part2node, num_nodes, din,
+                     num_parts, part_size, dim_worker, warp_per_block, st);               // :712-738
+}

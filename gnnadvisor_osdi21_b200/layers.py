@@ -1,0 +1,106 @@
+"""Autograd layer over the extension surface -- host-side mirror of GNNAdvisor/gnn_conv.py.
+
+Same class names and call conventions as the reference (ScatterAndGather :7-28, GNNAFunction
+:31-78, GCNConv :80-98, GNNAFunction_GIN :101-126, GINConv :128-147) so a script written against
+the reference's gnn_conv can import this module instead.  `inputInfo` is any object carrying
+row_pointers, column_index, degrees, partPtr, part2Node, partSize, dimWorker, warpPerBlock
+(param.InputProperty here, inputProperty in the reference).
+"""
+import math
+
+import torch
+
+from . import ops as GNNA
+
+
+def _graph(info):
+    return (info.row_pointers, info.column_index)
+
+
+def _tune(info):
+    return (info.partSize, info.dimWorker, info.warpPerBlock)
+
+
+class ScatterAndGather(torch.autograd.Function):
+    """out = A @ X; the graph is undirected so the backward is the same aggregation (gnn_conv.py:7-28)."""
+
+    @staticmethod
+    def forward(ctx, X, inputInfo):
+        ctx.inputInfo = inputInfo
+        ctx.tune = _tune(inputInfo)
+        return GNNA.SAG(X, *_graph(inputInfo), inputInfo.degrees, inputInfo.partPtr, inputInfo.part2Node, *ctx.tune)
+
+    @staticmethod
+    def backward(ctx, d_output):
+        info = ctx.inputInfo
+        d_input = GNNA.SAG(d_output.contiguous(), *_graph(info), info.degrees, info.partPtr, info.part2Node, *ctx.tune)
+        return d_input, None
+
+
+class GNNAFunction(torch.autograd.Function):
+    """GCN layer: update then aggregate (gnn_conv.py:31-78)."""
+
+    @staticmethod
+    def forward(ctx, X, weight, inputInfo):
+        ctx.save_for_backward(X, weight)
+        ctx.inputInfo = inputInfo
+        ctx.tune = _tune(inputInfo)
+        return GNNA.forward(X, weight, *_graph(inputInfo), inputInfo.degrees,
+                            inputInfo.partPtr, inputInfo.part2Node, *ctx.tune)[0]
+
+    @staticmethod
+    def backward(ctx, d_output):
+        X, weight = ctx.saved_tensors
+        info = ctx.inputInfo
+        d_input, d_weight = GNNA.backward(d_output.contiguous(), X, weight, *_graph(info), info.degrees,
+                                          info.partPtr, info.part2Node, *ctx.tune)
+        return d_input, d_weight, None
+
+
+class GNNAFunction_GIN(torch.autograd.Function):
+    """GIN layer: aggregate then update; the aggregated features are what backward needs (gnn_conv.py:101-126)."""
+
+    @staticmethod
+    def forward(ctx, X, weight, inputInfo, eplison):
+        X_prime, X_agg = GNNA.forward_gin(X, weight, *_graph(inputInfo), eplison,
+                                          inputInfo.partPtr, inputInfo.part2Node, *_tune(inputInfo))
+        ctx.save_for_backward(X_agg, weight)
+        ctx.inputInfo = inputInfo
+        ctx.tune = _tune(inputInfo)
+        ctx.eplison = eplison
+        return X_prime
+
+    @staticmethod
+    def backward(ctx, d_output):
+        X_agg, weight = ctx.saved_tensors
+        info = ctx.inputInfo
+        d_input, d_weight = GNNA.backward_gin(d_output.contiguous(), X_agg, weight, *_graph(info), ctx.eplison,
+                                              info.partPtr, info.part2Node, *ctx.tune)
+        return d_input, d_weight, None, None
+
+
+class _ConvBase(torch.nn.Module):
+    def __init__(self, input_dim, output_dim):
+        super().__init__()
+        self.weights = torch.nn.Parameter(torch.empty(input_dim, output_dim))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # U(-1/sqrt(out), 1/sqrt(out))  (gnn_conv.py:86-88, 136-138)
+        bound = 1.0 / math.sqrt(self.weights.size(1))
+        with torch.no_grad():
+            self.weights.uniform_(-bound, bound)
+
+
+class GCNConv(_ConvBase):
+    def forward(self, X, inputInfo):
+        return GNNAFunction.apply(X, self.weights, inputInfo)
+
+
+class GINConv(_ConvBase):
+    def __init__(self, input_dim, output_dim):
+        super().__init__(input_dim, output_dim)
+        self.eplison = 0.5          # fixed in the reference (gnn_conv.py:132); spelling kept
+
+    def forward(self, X, inputInfo):
+        return GNNAFunction_GIN.apply(X, self.weights, inputInfo, self.eplison)

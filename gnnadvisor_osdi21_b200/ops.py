@@ -1,0 +1,273 @@
+"""The `GNNAdvisor` extension surface on top of libgnna_b200.so.
+
+Mirrors, name for name and argument for argument, what the reference's pybind module exports
+(GNNAdvisor/GNNConv/GNNAdvisor.cpp:253-263) so that the reference's own gnn_conv.py / unitest.py /
+GNNA_main.py run unchanged against it (`import GNNAdvisor` -> compat/GNNAdvisor.py re-exports this):
+
+    SAG(X, row_ptr, col_idx, degrees, partPtr, part2Node, partSize, dimWorker, warpPerBlock) -> Tensor
+    forward(X, W, row_ptr, col_idx, degrees, partPtr, part2Node, ps, dw, wpb)          -> [out]
+    backward(d_out, X, W, row_ptr, col_idx, degrees, partPtr, part2Node, ps, dw, wpb)  -> [d_X, d_W]
+    forward_gin(X, W, row_ptr, col_idx, eps, partPtr, part2Node, ps, dw, wpb)          -> [out, X_agg]
+    backward_gin(d_out, X_agg, W, row_ptr, col_idx, eps, partPtr, part2Node, ps, dw, wpb) -> [d_X, d_W]
+    build_part(partSize, indptr)                                                       -> [partPtr, part2Node]
+
+torch is plumbing here: it owns device memory and the current stream; every kernel is ours
+(cuBLAS SGEMM for the dense products, as torch::mm is in the reference).  Error behaviour follows
+the reference's CHECK_INPUT (GNNAdvisor.cpp:71-73): a non-CUDA or non-contiguous tensor raises
+RuntimeError("<name> must be a CUDA tensor" / "<name> must be contiguous").
+"""
+import ctypes
+import os
+import warnings
+
+import torch
+
+from . import _lib
+
+__all__ = ["SAG", "forward", "backward", "forward_gin", "backward_gin", "build_part",
+           "build_part_exact", "aggregate_bf16", "degrees_from_row_ptr", "launch_info"]
+
+
+def _check_input(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("%s must have dtype %s (got %s)" % (name, dtype, t.dtype))
+
+
+def _graph_args(row_pointers, column_index, part_pointers, part2Node, device):
+    for t, n in ((row_pointers, "row_pointers"), (column_index, "column_index"),
+                 (part_pointers, "part_pointers"), (part2Node, "part2Node")):
+        _check_input(t, n, torch.int32)
+        if t.device != device:
+            raise RuntimeError("%s is on %s but the features are on %s" % (n, t.device, device))
+    if part2Node.numel() > 0 and part_pointers.numel() != part2Node.numel() + 1:
+        raise RuntimeError("part_pointers must have part2Node.numel()+1 entries")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _feat2d(t, name):
+    _check_input(t, name, torch.float32)
+    if t.dim() != 2:
+        raise RuntimeError("%s must be 2-D [num_nodes, dim]" % name)
+
+
+def SAG(input, row_pointers, column_index, degrees, part_pointers, part2Node, partSize, dimWorker, warpPerBlock):
+    """out = A @ input (unweighted neighbour sum).  Reference: SAG, GNNAdvisor.cpp:75-96; kernel.cu:110-259.
+    `degrees` is checked like the reference does but not used by the computation (as in the reference)."""
+    _feat2d(input, "input")
+    _check_input(degrees, "degrees")
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, input.device)
+    n, d = input.shape
+    out = torch.empty_like(input)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.load().gnna_sag_f32(_ptr(input), _ptr(out), _ptr(row_pointers), _ptr(column_index),
+                                            _ptr(part_pointers), _ptr(part2Node), n, d, part2Node.numel(),
+                                            int(partSize), int(dimWorker), int(warpPerBlock), _stream()), "SAG")
+    return out
+
+
+def forward(input, weight, row_pointers, column_index, degrees, part_pointers, part2Node,
+            partSize, dimWorker, warpPerBlock):
+    """GCN forward: out = Ahat @ (input @ weight).  Reference: spmm_forward, GNNAdvisor.cpp:99-122; kernel.cu:267-415."""
+    _feat2d(input, "input")
+    _feat2d(weight, "weight")
+    _check_input(degrees, "degrees", torch.float32)
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, input.device)
+    n, din = input.shape
+    if weight.shape[0] != din:
+        raise RuntimeError("size mismatch: input [%d, %d] x weight [%d, %d]" % (n, din, weight.shape[0], weight.shape[1]))
+    dout = weight.shape[1]
+    tmp = torch.empty((n, dout), dtype=torch.float32, device=input.device)
+    out = torch.empty((n, dout), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.load().gnna_forward_f32(_ptr(input), _ptr(weight), _ptr(tmp), _ptr(out),
+                                                _ptr(row_pointers), _ptr(column_index), _ptr(degrees),
+                                                _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                int(partSize), int(dimWorker), int(warpPerBlock), _stream()), "forward")
+    return [out]
+
+
+def backward(d_output, X, W, row_pointers, column_index, degrees, part_pointers, part2Node,
+             partSize, dimWorker, warpPerBlock):
+    """GCN backward: G = Ahat @ d_output; returns [G @ W^T, X^T @ G].
+    Reference: spmm_backward, GNNAdvisor.cpp:124-150; kernel.cu:422-552."""
+    _feat2d(d_output, "d_output")
+    _feat2d(X, "X")
+    _feat2d(W, "W")
+    _check_input(degrees, "degrees", torch.float32)
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, d_output.device)
+    n, dout = d_output.shape
+    din = X.shape[1]
+    if X.shape[0] != n or W.shape[0] != din or W.shape[1] != dout:
+        raise RuntimeError("size mismatch: d_output %s, X %s, W %s" % (tuple(d_output.shape), tuple(X.shape), tuple(W.shape)))
+    g = torch.empty_like(d_output)
+    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device)
+    d_weight = torch.empty((din, dout), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().gnna_backward_f32(_ptr(d_output), _ptr(X), _ptr(W), _ptr(g), _ptr(d_input), _ptr(d_weight),
+                                                 _ptr(row_pointers), _ptr(column_index), _ptr(degrees),
+                                                 _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                 int(partSize), int(dimWorker), int(warpPerBlock), _stream()), "backward")
+    return [d_input, d_weight]
+
+
+def forward_gin(input, weight, row_pointers, column_index, epsilon, part_pointers, part2Node,
+                partSize, dimWorker, warpPerBlock):
+    """GIN forward: X_agg = eps * (A @ input); out = X_agg @ weight; returns [out, X_agg].
+    Reference: spmm_forward_gin, GNNAdvisor.cpp:156-178; kernel.cu:559-689."""
+    _feat2d(input, "input")
+    _feat2d(weight, "weight")
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, input.device)
+    n, din = input.shape
+    if weight.shape[0] != din:
+        raise RuntimeError("size mismatch: input [%d, %d] x weight [%d, %d]" % (n, din, weight.shape[0], weight.shape[1]))
+    dout = weight.shape[1]
+    x_agg = torch.empty_like(input)
+    out = torch.empty((n, dout), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.load().gnna_forward_gin_f32(_ptr(input), _ptr(weight), float(epsilon), _ptr(out), _ptr(x_agg),
+                                                    _ptr(row_pointers), _ptr(column_index),
+                                                    _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                    int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+                   "forward_gin")
+    return [out, x_agg]
+
+
+def backward_gin(d_output, X, W, row_pointers, column_index, epsilon, part_pointers, part2Node,
+                 partSize, dimWorker, warpPerBlock):
+    """GIN backward (X is the saved X_agg): d_W = X^T @ d_output; d_X = eps * A @ (d_output @ W^T).
+    Reference: spmm_backward_gin, GNNAdvisor.cpp:183-207; kernel.cu:696-814."""
+    _feat2d(d_output, "d_output")
+    _feat2d(X, "X")
+    _feat2d(W, "W")
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, d_output.device)
+    n, dout = d_output.shape
+    din = X.shape[1]
+    if X.shape[0] != n or W.shape[0] != din or W.shape[1] != dout:
+        raise RuntimeError("size mismatch: d_output %s, X %s, W %s" % (tuple(d_output.shape), tuple(X.shape), tuple(W.shape)))
+    pm = torch.empty((n, din), dtype=torch.float32, device=X.device)
+    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device)
+    d_weight = torch.empty((din, dout), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().gnna_backward_gin_f32(_ptr(d_output), _ptr(X), _ptr(W), float(epsilon), _ptr(pm),
+                                                     _ptr(d_input), _ptr(d_weight),
+                                                     _ptr(row_pointers), _ptr(column_index),
+                                                     _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                     int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+                   "backward_gin")
+    return [d_input, d_weight]
+
+
+def aggregate_bf16(mode, X_bf16, row_pointers, column_index, degrees, epsilon, part_pointers, part2Node,
+                   partSize, dimWorker, warpPerBlock):
+    """Extension (no reference counterpart): gather bf16 rows, fp32 accumulate, fp32 out.
+    mode: 0 SAG, 1 GCN-normalised, 2 GIN."""
+    _check_input(X_bf16, "X", torch.bfloat16)
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, X_bf16.device)
+    if mode == 1:
+        _check_input(degrees, "degrees", torch.float32)
+    n, d = X_bf16.shape
+    out = torch.empty((n, d), dtype=torch.float32, device=X_bf16.device)
+    with torch.cuda.device(X_bf16.device):
+        _lib.check(_lib.load().gnna_aggregate_bf16(int(mode), _ptr(X_bf16), _ptr(out), _ptr(row_pointers), _ptr(column_index),
+                                                   _ptr(degrees) if mode == 1 else ctypes.c_void_p(0), float(epsilon),
+                                                   _ptr(part_pointers), _ptr(part2Node), n, d, part2Node.numel(),
+                                                   int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+                   "aggregate_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ build_part
+_F32_EXACT_LIMIT = 1 << 24
+
+
+def _build_part_host(partSize, indptr, compat):
+    if indptr.dtype != torch.int32 or indptr.dim() != 1:
+        # the reference takes accessor<int,1>, which throws for anything else (GNNAdvisor.cpp:215)
+        raise RuntimeError("expected a 1-D int32 (torch.IntTensor) indptr, got %s with %d dims" % (indptr.dtype, indptr.dim()))
+    if partSize <= 0:
+        raise RuntimeError("partSize must be positive")
+    indptr = indptr.contiguous()
+    n = indptr.numel() - 1
+    lib = _lib.load()
+    P = lib.gnna_count_parts_host(int(partSize), ctypes.c_void_p(indptr.data_ptr()), n)
+    if P < 0:
+        _lib.check(-1, "build_part")
+    pp = torch.empty(P + 1, dtype=torch.int32)
+    pn = torch.empty(P, dtype=torch.int32)
+    _lib.check(lib.gnna_build_part_host(int(partSize), ctypes.c_void_p(indptr.data_ptr()), n,
+                                        ctypes.c_void_p(pp.data_ptr()), ctypes.c_void_p(pn.data_ptr()), P,
+                                        1 if compat else 0), "build_part")
+    return pp, pn
+
+
+def build_part(partSize, indptr):
+    """Neighbour-group table.  Reference: build_part, GNNAdvisor.cpp:210-251.
+
+    CPU int32 indptr (what GNNA_main.py:102 passes): returns what the reference returns, bit for bit --
+    two float32 CPU tensors, including the reference's terminal-entry rule when the last node is
+    isolated -- as long as every offset is exactly representable in float32
+    (< 2^24).  Beyond that the reference's float table is silently corrupt (F5); we return the exact
+    int32 table instead (the caller's `.int()` is then a no-op) and warn once.
+    Set GNNA_BUILD_PART=exact to always get the exact int32 table (terminal = indptr[-1]).
+    CUDA indptr: the table is built on the GPU, exact, returned as int32 CUDA tensors."""
+    if indptr.is_cuda:
+        return build_part_exact(partSize, indptr)
+    if os.environ.get("GNNA_BUILD_PART", "compat") == "exact":
+        return build_part_exact(partSize, indptr)
+    n_edges = int(indptr[-1]) if indptr.numel() > 0 else 0
+    if max(n_edges, indptr.numel()) >= _F32_EXACT_LIMIT:
+        warnings.warn("build_part: offsets exceed 2^24; returning exact int32 tables "
+                      "(the reference's float32 tables are rounded here)", stacklevel=2)
+        return build_part_exact(partSize, indptr)
+    pp, pn = _build_part_host(partSize, indptr, compat=True)
+    return [pp.float(), pn.float()]
+
+
+def build_part_exact(partSize, indptr):
+    """Integer-exact int32 table (terminal always = indptr[-1]); on the device when indptr is CUDA."""
+    if not indptr.is_cuda:
+        pp, pn = _build_part_host(partSize, indptr, compat=False)
+        return [pp, pn]
+    _check_input(indptr, "indptr", torch.int32)
+    lib = _lib.load()
+    n = indptr.numel() - 1
+    ws = torch.empty(int(lib.gnna_build_part_workspace_bytes(n)), dtype=torch.uint8, device=indptr.device)
+    P = ctypes.c_int64(0)
+    with torch.cuda.device(indptr.device):
+        _lib.check(lib.gnna_build_part_device(int(partSize), _ptr(indptr), n, ctypes.c_void_p(0), ctypes.c_void_p(0),
+                                              ctypes.byref(P), _ptr(ws), ws.numel(), _stream()), "build_part(device)")
+        pp = torch.empty(P.value + 1, dtype=torch.int32, device=indptr.device)
+        pn = torch.empty(P.value, dtype=torch.int32, device=indptr.device)
+        _lib.check(lib.gnna_build_part_device(int(partSize), _ptr(indptr), n, _ptr(pp), _ptr(pn),
+                                              ctypes.byref(P), _ptr(ws), ws.numel(), _stream()), "build_part(device)")
+    return [pp, pn]
+
+
+def degrees_from_row_ptr(row_pointers):
+    """degrees = sqrt(max(deg, 1)) as float32 on the device (GNNAdvisor/dataset.py:11-18,121-122)."""
+    _check_input(row_pointers, "row_pointers", torch.int32)
+    n = row_pointers.numel() - 1
+    out = torch.empty(n, dtype=torch.float32, device=row_pointers.device)
+    with torch.cuda.device(row_pointers.device):
+        _lib.check(_lib.load().gnna_degrees(_ptr(row_pointers), n, _ptr(out), _stream()), "degrees")
+    return out
+
+
+def launch_info(dim, num_parts, dimWorker, warpPerBlock, elem_bytes=4):
+    info = _lib.LaunchInfo()
+    _lib.check(_lib.load().gnna_query_launch(int(elem_bytes), int(dim), int(num_parts), int(dimWorker), int(warpPerBlock),
+                                             ctypes.byref(info)), "query_launch")
+    return {f: getattr(info, f) for f, _ in _lib.LaunchInfo._fields_}

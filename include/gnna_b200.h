@@ -1,0 +1,171 @@
+/*
+ * gnna_b200.h -- C ABI of the B200-native GNNAdvisor aggregation runtime (libgnna_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of YukeWang96/GNNAdvisor_OSDI21: the
+ * neighbour-partitioned SpMM aggregation behind the `GNNAdvisor` extension module
+ * (reference: GNNAdvisor/GNNConv/GNNAdvisor.cpp:253-263 exports SAG, forward, backward,
+ * forward_gin, backward_gin, build_part).  Each entry point below names the reference
+ * function it replaces.  Signatures carry only plain pointers and sizes; the Python module
+ * `GNNAdvisor` (gnnadvisor_osdi21_b200/compat/GNNAdvisor.py) is a thin ctypes binding that
+ * allocates outputs with torch and passes raw device pointers + the current CUDA stream.
+ *
+ * Conventions
+ *   - all feature matrices are row-major contiguous; `f32` = float, `bf16` = __nv_bfloat16 bits
+ *   - index arrays are int32 (the reference's IntTensor contract, GNNA_main.py:107-110)
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_host`
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *     the reference launches on, GNNAdvisor_kernel.cu:149,298)
+ *   - every call is asynchronous w.r.t. the host (like the reference) and returns GNNA_OK or a
+ *     negative error code; gnna_last_error() gives the message (the reference printf()s and
+ *     exit(-1)s on a launch error, kernel.cu:177-181 -- we return the error instead)
+ *   - part_size / dim_worker / warp_per_block keep the reference's meaning (param.py:27-29):
+ *     neighbours per group / lanes that cooperate on one neighbour row / warps per CTA.
+ *     dim_worker <= 0 or warp_per_block <= 0 selects the built-in B200 choice.
+ *   - a group with part_ptr[w+1] <= part_ptr[w] contributes nothing (kernel.cu:383).
+ */
+#ifndef GNNA_B200_H
+#define GNNA_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GNNA_API __attribute__((visibility("default")))
+#else
+#define GNNA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNA_OK 0
+#define GNNA_ERR_INVALID (-1)   /* bad argument (null pointer, non-positive size, ...) */
+#define GNNA_ERR_CUDA (-2)      /* CUDA runtime / launch error */
+#define GNNA_ERR_CUBLAS (-3)    /* cuBLAS error in one of the dense products */
+#define GNNA_ERR_UNSUPPORTED (-4)
+
+/* Library identification and error text (thread-local). */
+GNNA_API int gnna_abi_version(void);
+GNNA_API const char *gnna_last_error(void);
+
+/* ---- neighbour-group table ---------------------------------------------------------------
+ * replaces build_part(int partSize, Tensor indptr)      GNNAdvisor.cpp:210-251
+ * Pass 1 (:219-227): number of groups P = sum_i ceil(deg_i / part_size).                  */
+GNNA_API int64_t gnna_count_parts_host(int part_size, const int32_t *indptr_host, int64_t num_nodes);
+
+/* Pass 2 (:229-249) on the host, multi-threaded.  part_ptr_host has P+1 entries, part2node_host P.
+ * compat != 0 reproduces the reference bit for bit after the caller's `.int()` cast
+ * (float32 round-trip of every entry = F5, terminal left 0 when the last node is isolated = F6);
+ * compat == 0 writes the integer-exact table the reference intends.                        */
+GNNA_API int gnna_build_part_host(int part_size, const int32_t *indptr_host, int64_t num_nodes,
+                         int32_t *part_ptr_host, int32_t *part2node_host, int64_t num_parts,
+                         int compat);
+
+/* Same table built on the device (scan + binary-search expand), integer-exact.
+ * `num_parts_out_host` receives P (one 8-byte D2H copy, synchronises `stream`); call once with
+ * part_ptr == NULL to size the outputs, then again with buffers of P+1 / P entries.        */
+GNNA_API int gnna_build_part_device(int part_size, const int32_t *indptr, int64_t num_nodes,
+                           int32_t *part_ptr, int32_t *part2node, int64_t *num_parts_out_host,
+                           void *workspace, int64_t workspace_bytes, void *stream);
+GNNA_API int64_t gnna_build_part_workspace_bytes(int64_t num_nodes);
+
+/* degrees[i] = sqrtf(max(deg_i, 1))                    GNNAdvisor/dataset.py:11-18,121-122 */
+GNNA_API int gnna_degrees(const int32_t *indptr, int64_t num_nodes, float *degrees, void *stream);
+
+/* ---- aggregation kernels -------------------------------------------------------------------
+ * One launch each; `out` is fully written (no pre-zeroing needed by the caller).
+ *
+ * replaces SAG_cuda + SAG_cuda_kernel                  GNNAdvisor_kernel.cu:110-259
+ *   out[i,:] = sum_{j in N(i)} X[j,:]                                                      */
+GNNA_API int gnna_sag_f32(const float *X, float *out,
+                 const int32_t *row_ptr, const int32_t *col_idx,
+                 const int32_t *part_ptr, const int32_t *part2node,
+                 int64_t num_nodes, int dim, int64_t num_parts,
+                 int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* replaces spmm_forward_cuda_kernel / spmm_backward_cuda_kernel   kernel.cu:324-415, 478-552
+ *   out[i,:] = sum_{j in N(i)} fl( fl(degrees[i]*degrees[j]) * X[j,:] )                     */
+GNNA_API int gnna_gcn_aggregate_f32(const float *X, float *out,
+                           const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                           const int32_t *part_ptr, const int32_t *part2node,
+                           int64_t num_nodes, int dim, int64_t num_parts,
+                           int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* replaces spmm_forward_cuda_kernel_gin / spmm_backward_cuda_kernel_gin  kernel.cu:620-689, 749-814
+ *   out[i,:] = sum over groups g of node i of fl( eps * sum_{j in g} X[j,:] )               */
+GNNA_API int gnna_gin_aggregate_f32(const float *X, float *out,
+                           const int32_t *row_ptr, const int32_t *col_idx, float eps,
+                           const int32_t *part_ptr, const int32_t *part2node,
+                           int64_t num_nodes, int dim, int64_t num_parts,
+                           int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* bf16-storage variant: neighbour rows are gathered as bf16 (half the gather bytes), summed in
+ * fp32 and written as fp32.  An extension: the reference is fp32-only.
+ * mode: 0 = SAG, 1 = GCN (degrees), 2 = GIN (eps).                                           */
+GNNA_API int gnna_aggregate_bf16(int mode, const void *X_bf16, float *out_f32,
+                        const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
+                        const int32_t *part_ptr, const int32_t *part2node,
+                        int64_t num_nodes, int dim, int64_t num_parts,
+                        int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* ---- the four layer operators (aggregation + the dense products around it) -----------------
+ * Dense products are fp32 cuBLAS SGEMM (no TF32), as torch::mm is in the reference.
+ *
+ * replaces spmm_forward_cuda          kernel.cu:267-322   T = X*W ; out = Ahat*T
+ *   X [N,din], W [din,dout], T_ws [N,dout] scratch, out [N,dout]                            */
+GNNA_API int gnna_forward_f32(const float *X, const float *W, float *T_ws, float *out,
+                     const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                     const int32_t *part_ptr, const int32_t *part2node,
+                     int64_t num_nodes, int din, int dout, int64_t num_parts,
+                     int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* replaces spmm_backward_cuda         kernel.cu:422-476   G = Ahat*dOut ; dX = G*W^T ; dW = X^T*G
+ *   d_out [N,dout], G_ws [N,dout] scratch, d_input [N,din] (may be NULL: skip it), d_weight [din,dout] */
+GNNA_API int gnna_backward_f32(const float *d_out, const float *X, const float *W, float *G_ws,
+                      float *d_input, float *d_weight,
+                      const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                      const int32_t *part_ptr, const int32_t *part2node,
+                      int64_t num_nodes, int din, int dout, int64_t num_parts,
+                      int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* replaces spmm_forward_cuda_gin      kernel.cu:559-617   S = eps*A*X ; out = S*W
+ *   x_agg [N,din] receives S (saved for backward, gnn_conv.py:109), out [N,dout]            */
+GNNA_API int gnna_forward_gin_f32(const float *X, const float *W, float eps, float *out, float *x_agg,
+                         const int32_t *row_ptr, const int32_t *col_idx,
+                         const int32_t *part_ptr, const int32_t *part2node,
+                         int64_t num_nodes, int din, int dout, int64_t num_parts,
+                         int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* replaces spmm_backward_cuda_gin     kernel.cu:696-747   dW = S^T*dOut ; Pm = dOut*W^T ; dX = eps*A*Pm
+ *   Pm_ws [N,din] scratch, d_input [N,din], d_weight [din,dout]                             */
+GNNA_API int gnna_backward_gin_f32(const float *d_out, const float *x_agg, const float *W, float eps,
+                          float *Pm_ws, float *d_input, float *d_weight,
+                          const int32_t *row_ptr, const int32_t *col_idx,
+                          const int32_t *part_ptr, const int32_t *part2node,
+                          int64_t num_nodes, int din, int dout, int64_t num_parts,
+                          int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* ---- introspection (for tests, bench.py and the tuner) ------------------------------------
+ * Launch geometry the library would use for a given call: fills lanes_per_row, chunks_per_lane,
+ * vec_width, warps_per_block, grid_x, grid_y.  Returns GNNA_OK.                             */
+typedef struct gnna_launch_info {
+    int vec_width;        /* elements per load: 4, 2 or 1 (fp32); 8, 4, 2, 1 (bf16) */
+    int lanes_per_row;    /* lanes cooperating on one neighbour row (dim_worker, power of two) */
+    int chunks_per_lane;  /* vector chunks each lane owns inside one d-tile */
+    int warps_per_block;
+    int groups_per_warp;  /* 32 / lanes_per_row */
+    int64_t grid_x;
+    int grid_y;           /* d-tiles */
+    int kernels;          /* kernel launches this aggregation issues (memset node excluded) */
+} gnna_launch_info;
+GNNA_API int gnna_query_launch(int elem_bytes, int dim, int64_t num_parts, int dim_worker, int warp_per_block,
+                      gnna_launch_info *info);
+
+/* Number of kernels this library has launched on this thread since the last reset
+ * (bench.py's "gpu_launches" is read from here, not guessed). */
+GNNA_API int64_t gnna_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNA_B200_H */

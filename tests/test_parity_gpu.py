@@ -1,0 +1,343 @@
+"""GPU parity tests: the CUDA path (through the ctypes binding of the C ABI) against the CPU oracle on
+the same seeded inputs, against golden outputs of the reference's own CUDA kernels, and -- at the
+sizes of BASELINE.json's configurations -- through size-independent properties.
+
+Tolerance: 1e-4 relative fp32 (BASELINE.json north_star), see helpers.assert_close.
+Integer work (build_part on the device) is compared bit for bit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import assert_close, make_graph, rand_features, rand_weight
+from gnnadvisor_osdi21_b200 import graph, ops, layers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+class G:
+    """A graph + its group table on the device, with the numpy copies for the oracle."""
+
+    def __init__(self, rp, ci, ps, exact=True):
+        self.rp, self.ci, self.ps = rp, ci, ps
+        self.pp, self.pn = oracle.build_part(ps, rp, exact=exact)
+        self.deg = oracle.degrees(rp)
+        self.n = len(rp) - 1
+        self.d_rp, self.d_ci, self.d_pp, self.d_pn, self.d_deg = dev(rp), dev(ci), dev(self.pp), dev(self.pn), dev(self.deg)
+
+    def gargs(self):
+        return (self.d_rp, self.d_ci)
+
+    def pargs(self):
+        return (self.d_pp, self.d_pn)
+
+
+GRAPHS = {
+    "uniform": lambda: make_graph("uniform", 700, 4000, 21),
+    "rmat": lambda: make_graph("rmat", 1500, 40000, 22),
+}
+
+
+@pytest.mark.parametrize("gname", sorted(GRAPHS))
+@pytest.mark.parametrize("dim", [1, 2, 3, 4, 6, 7, 16, 32, 41, 47, 64, 100, 128, 172, 300])
+def test_aggregation_modes_all_dims(gname, dim):
+    """SAG / GCN / GIN aggregation at the dims of every BASELINE.json config (and awkward ones)."""
+    rp, ci = GRAPHS[gname]()
+    g = G(rp, ci, 32)
+    X = rand_features(g.n, dim, 100 + dim)
+    dX = dev(X)
+    out = ops.SAG(dX, *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 8)
+    assert_close(out.cpu().numpy(), oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="SAG")
+    lib_gcn = _gcn_agg(dX, g, 32, 8)
+    assert_close(lib_gcn, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="GCN")
+    lib_gin = _gin_agg(dX, g, 0.5, 32, 8)
+    assert_close(lib_gin, oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn), what="GIN")
+
+
+def _gcn_agg(dX, g, dw, wpb):
+    """GCN aggregation alone: forward() with W = identity would add a GEMM, so call the C ABI entry."""
+    import ctypes
+    from gnnadvisor_osdi21_b200 import _lib
+    out = torch.empty_like(dX)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().gnna_gcn_aggregate_f32(p(dX), p(out), p(g.d_rp), p(g.d_ci), p(g.d_deg), p(g.d_pp), p(g.d_pn),
+                                                  g.n, dX.shape[1], g.d_pn.numel(), g.ps, dw, wpb,
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "gcn")
+    return out.cpu().numpy()
+
+
+def _gin_agg(dX, g, eps, dw, wpb):
+    import ctypes
+    from gnnadvisor_osdi21_b200 import _lib
+    out = torch.empty_like(dX)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().gnna_gin_aggregate_f32(p(dX), p(out), p(g.d_rp), p(g.d_ci), eps, p(g.d_pp), p(g.d_pn),
+                                                  g.n, dX.shape[1], g.d_pn.numel(), g.ps, dw, wpb,
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "gin")
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("ps", [1, 2, 5, 16, 32, 64, 512])
+@pytest.mark.parametrize("dw", [1, 2, 4, 8, 16, 32])
+def test_partsize_dimworker_sweep(ps, dw):
+    """The study scripts sweep partSize 2..512 and dimWorker 1..32 (s7-4_1, s7-4_2): any combination is valid."""
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, ps)
+    X = rand_features(g.n, 64, 7)
+    assert_close(_gcn_agg(dev(X), g, dw, 4), oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="ps%d dw%d" % (ps, dw))
+
+
+@pytest.mark.parametrize("wpb", [1, 2, 3, 8, 16, 32])
+def test_warp_per_block_sweep(wpb):
+    rp, ci = GRAPHS["uniform"]()
+    g = G(rp, ci, 8)
+    X = rand_features(g.n, 16, 8)
+    out = ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 8, 16, wpb)
+    assert_close(out.cpu().numpy(), oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="wpb%d" % wpb)
+
+
+def test_single_group_nodes_are_bit_identical():
+    """A node whose neighbours fit one group is summed in the reference's order: exact equality."""
+    rp, ci = make_graph("uniform", 2000, 12000, 31)
+    assert (rp[1:] - rp[:-1]).max() <= 32
+    g = G(rp, ci, 32)
+    X = rand_features(g.n, 64, 9)
+    for mode, ref in ((1, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn)), (2, oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn))):
+        got = _gcn_agg(dev(X), g, 32, 8) if mode == 1 else _gin_agg(dev(X), g, 0.5, 32, 8)
+        assert np.array_equal(got, ref), "mode %d" % mode
+
+
+def test_layer_operators_against_oracle():
+    """forward / backward / forward_gin / backward_gin incl. the dense products (cuBLAS SGEMM)."""
+    for (n, e, din, dout, ps) in [(900, 12000, 96, 16, 32), (900, 12000, 16, 7, 8), (600, 9000, 64, 64, 32)]:
+        rp, ci = make_graph("rmat", n, e, 41)
+        g = G(rp, ci, ps)
+        X, W, dO = rand_features(n, din, 42), rand_weight(din, dout, 43), rand_features(n, dout, 44)
+        dXd, dWd, dOd = dev(X), dev(W), dev(dO)
+        out, = ops.forward(dXd, dWd, *g.gargs(), g.d_deg, *g.pargs(), ps, 32, 8)
+        assert_close(out.cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], what="forward")
+        dX, dW = ops.backward(dOd, dXd, dWd, *g.gargs(), g.d_deg, *g.pargs(), ps, 32, 8)
+        odX, odW = oracle.backward(dO, X, W, rp, ci, g.deg, g.pp, g.pn)
+        assert_close(dX.cpu().numpy(), odX, what="backward dX")
+        assert_close(dW.cpu().numpy(), odW, what="backward dW")
+        o, S = ops.forward_gin(dXd, dWd, *g.gargs(), 0.5, *g.pargs(), ps, 32, 2)
+        oo, oS = oracle.forward_gin(X, W, rp, ci, 0.5, g.pp, g.pn)
+        assert_close(S.cpu().numpy(), oS, what="gin agg")
+        assert_close(o.cpu().numpy(), oo, what="gin out")
+        dXg, dWg = ops.backward_gin(dOd, S, dWd, *g.gargs(), 0.5, *g.pargs(), ps, 32, 2)
+        odXg, odWg = oracle.backward_gin(dO, oS, W, rp, ci, 0.5, g.pp, g.pn)
+        assert_close(dXg.cpu().numpy(), odXg, what="gin dX")
+        assert_close(dWg.cpu().numpy(), odWg, what="gin dW")
+
+
+def test_reference_cuda_golden(golden_dir):
+    """Outputs of the reference's own kernels on a B200 (tests/golden/refgpu.npz)."""
+    path = os.path.join(golden_dir, "refgpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/refgpu.npz not generated yet")
+    gz = np.load(path)
+    for c in range(len({k.split("/")[0] for k in gz.files})):
+        k = "case%d/" % c
+        din, dout, ps, dw, wpb = [int(v) for v in gz[k + "meta"]]
+        rp, ci = gz[k + "row_ptr"], gz[k + "col_idx"]
+        pp, pn = dev(gz[k + "partPtr"]), dev(gz[k + "part2Node"])
+        d_rp, d_ci = dev(rp), dev(ci)
+        deg = ops.degrees_from_row_ptr(d_rp)
+        X, W, dO = dev(gz[k + "X"]), dev(gz[k + "W"]), dev(gz[k + "dO"])
+        assert_close(ops.SAG(X, d_rp, d_ci, deg, pp, pn, ps, dw, wpb).cpu().numpy(), gz[k + "SAG"], what=k + "SAG")
+        assert_close(ops.forward(X, W, d_rp, d_ci, deg, pp, pn, ps, dw, wpb)[0].cpu().numpy(), gz[k + "forward"], what=k + "forward")
+        dX, dW = ops.backward(dO, X, W, d_rp, d_ci, deg, pp, pn, ps, dw, wpb)
+        assert_close(dX.cpu().numpy(), gz[k + "backward_dX"], what=k + "dX")
+        assert_close(dW.cpu().numpy(), gz[k + "backward_dW"], what=k + "dW")
+        o, S = ops.forward_gin(X, W, d_rp, d_ci, 0.5, pp, pn, ps, dw, wpb)
+        assert_close(S.cpu().numpy(), gz[k + "forward_gin_agg"], what=k + "gin agg")
+        assert_close(o.cpu().numpy(), gz[k + "forward_gin"], what=k + "gin out")
+        dXg, dWg = ops.backward_gin(dO, dev(gz[k + "forward_gin_agg"]), W, d_rp, d_ci, 0.5, pp, pn, ps, dw, wpb)
+        assert_close(dXg.cpu().numpy(), gz[k + "backward_gin_dX"], what=k + "gin dX")
+        assert_close(dWg.cpu().numpy(), gz[k + "backward_gin_dW"], what=k + "gin dW")
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def test_empty_and_degenerate_graphs():
+    # no edges at all: every output row is zero, no groups
+    rp = np.zeros(11, dtype=np.int32)
+    g = G(rp, np.zeros(0, dtype=np.int32), 32)
+    X = rand_features(10, 16, 1)
+    assert g.pn.size == 0
+    out = ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4)
+    assert torch.count_nonzero(out).item() == 0
+    # one node with a self loop
+    g = G(np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), 32)
+    X = rand_features(1, 5, 2)
+    assert np.array_equal(ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4).cpu().numpy(), X)
+    # zero nodes
+    e = torch.empty(0, 8, device=DEV)
+    z = torch.zeros(1, dtype=torch.int32, device=DEV)
+    zi = torch.empty(0, dtype=torch.int32, device=DEV)
+    assert ops.SAG(e, z, zi, torch.empty(0, device=DEV), z, zi, 32, 32, 4).shape == (0, 8)
+
+
+def test_isolated_nodes_and_f6_table():
+    """Last node isolated: the reference table's terminal is 0 (F6), which makes the last group empty
+    (partEnd <= partBeg contributes nothing, kernel.cu:383).  With the exact table it is aggregated."""
+    rng = np.random.default_rng(3)
+    deg = rng.integers(0, 50, 400); deg[::5] = 0; deg[-1] = 0; deg[-2] = 40
+    rp = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    ci = rng.integers(0, 400, rp[-1]).astype(np.int32)
+    X = rand_features(400, 32, 4)
+    for exact in (True, False):
+        g = G(rp, ci, 32, exact=exact)
+        if not exact:
+            assert g.pp[-1] == 0
+        got = _gcn_agg(dev(X), g, 32, 4)
+        assert_close(got, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="exact=%s" % exact)
+        assert np.count_nonzero(got[deg == 0]) == 0
+    # the F6 table drops the last group's neighbours, the exact one does not
+    ge, gc = G(rp, ci, 32, exact=True), G(rp, ci, 32, exact=False)
+    a, b = _gcn_agg(dev(X), ge, 32, 4), _gcn_agg(dev(X), gc, 32, 4)
+    assert not np.allclose(a[-2], b[-2]) and np.array_equal(a[:-2], b[:-2])
+
+
+def test_hub_node_many_groups():
+    """One node with 50 000 neighbours (1 563 groups merged by vector reductions) among small ones."""
+    n = 60000
+    src = np.concatenate([np.zeros(50000, dtype=np.int64), np.arange(1, 50001)])
+    dst = np.concatenate([np.arange(1, 50001), np.zeros(50000, dtype=np.int64)])
+    rp, ci = graph.csr_from_edges(torch.from_numpy(src), torch.from_numpy(dst), n)
+    rp, ci = rp.numpy(), ci.numpy()
+    g = G(rp, ci, 32)
+    X = np.abs(rand_features(n, 16, 5)) + 0.5
+    assert_close(ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 8).cpu().numpy(),
+                 oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn, threads=-1), what="hub")
+
+
+def test_noncontiguous_and_wrong_dtype_inputs_raise():
+    rp, ci = GRAPHS["uniform"]()
+    g = G(rp, ci, 32)
+    X = dev(rand_features(g.n, 32, 1))
+    with pytest.raises(RuntimeError, match="input must be contiguous"):
+        ops.SAG(X[:, ::2], *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4)
+    with pytest.raises(RuntimeError, match="dtype"):
+        ops.SAG(X.double(), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4)
+    with pytest.raises(RuntimeError, match="column_index must be a CUDA tensor"):
+        ops.SAG(X, g.d_rp, g.d_ci.cpu(), g.d_deg, *g.pargs(), 32, 32, 4)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        ops.forward(X, torch.zeros(5, 3, device=DEV), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4)
+
+
+def test_inputs_are_not_modified_and_nonzero_stream():
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+    X = rand_features(g.n, 64, 6)
+    dX = dev(X)
+    keep = dX.clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = ops.SAG(dX, *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 8)
+    s.synchronize()
+    assert torch.equal(dX, keep)
+    assert_close(out.cpu().numpy(), oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="stream")
+
+
+# ------------------------------------------------------------------------------------------ device build_part / degrees
+def test_build_part_device_bit_exact():
+    rng = np.random.default_rng(11)
+    for n, hi in ((1, 5), (1000, 90), (300000, 40)):
+        deg = rng.integers(0, hi, n)
+        if n > 1000:
+            deg[rng.integers(0, n, 20)] = 30000
+        rp = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        for ps in (1, 3, 32):
+            pp, pn = ops.build_part(ps, dev(rp))
+            opp, opn = oracle.build_part(ps, rp, exact=True)
+            assert pp.is_cuda and pp.dtype == torch.int32
+            assert np.array_equal(pp.cpu().numpy(), opp) and np.array_equal(pn.cpu().numpy(), opn)
+    rp = np.array([0, 0, 3, 3, 10], dtype=np.int32)
+    assert np.array_equal(ops.degrees_from_row_ptr(dev(rp)).cpu().numpy(), oracle.degrees(rp))
+
+
+# ------------------------------------------------------------------------------------------ bf16 storage path
+@pytest.mark.parametrize("dim", [8, 16, 41, 64, 128, 200])
+def test_bf16_gather_path(dim):
+    """bf16 neighbour rows, fp32 accumulate: compared with the fp32 oracle on the SAME bf16-rounded
+    inputs (no reference of this precision exists) -- so the fp32 tolerance applies."""
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+    Xb = torch.from_numpy(rand_features(g.n, dim, 12)).to(torch.bfloat16)
+    Xr = Xb.float().numpy()
+    for mode in (0, 1, 2):
+        got = ops.aggregate_bf16(mode, Xb.to(DEV), *g.gargs(), g.d_deg, 0.5, *g.pargs(), 32, 32, 8).cpu().numpy()
+        assert_close(got, oracle.aggregate(mode, Xr, ci, g.deg, 0.5, g.pp, g.pn), what="bf16 mode %d" % mode)
+
+
+# ------------------------------------------------------------------------------------------ autograd layers
+def test_gcn_and_gin_layers_autograd():
+    """GCNConv / GINConv modules: forward value and the gradients the reference's backward defines."""
+    n, din, hid = 500, 24, 16
+    rp, ci = make_graph("rmat", n, 6000, 51)
+    g = G(rp, ci, 16)
+
+    class Info:
+        pass
+    info = Info()
+    info.row_pointers, info.column_index, info.degrees = g.d_rp, g.d_ci, g.d_deg
+    info.partPtr, info.part2Node = g.d_pp, g.d_pn
+    info.partSize, info.dimWorker, info.warpPerBlock = 16, 16, 4
+    X = rand_features(n, din, 52)
+    dO = rand_features(n, hid, 53)
+    for conv, fwd, bwd in ((layers.GCNConv(din, hid), oracle.forward, oracle.backward),
+                           (layers.GINConv(din, hid), None, None)):
+        conv = conv.to(DEV)
+        W = conv.weights.detach().cpu().numpy()
+        assert np.abs(W).max() <= 1.0 / np.sqrt(hid) + 1e-7
+        x = dev(X).requires_grad_(True)
+        y = conv(x, info)
+        y.backward(dev(dO))
+        if fwd is not None:
+            assert_close(y.detach().cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], what="gcn y")
+            odX, odW = oracle.backward(dO, X, W, rp, ci, g.deg, g.pp, g.pn)
+        else:
+            oy, oS = oracle.forward_gin(X, W, rp, ci, 0.5, g.pp, g.pn)
+            assert_close(y.detach().cpu().numpy(), oy, what="gin y")
+            odX, odW = oracle.backward_gin(dO, oS, W, rp, ci, 0.5, g.pp, g.pn)
+        assert_close(x.grad.cpu().numpy(), odX, what="dX")
+        assert_close(conv.weights.grad.cpu().numpy(), odW, what="dW")
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("name,dim,scale", [("reddit", 64, 0.25), ("ogbn-products", 64, 0.1)])
+def test_full_size_properties(name, dim, scale):
+    """At (a fraction of) BASELINE.json's sizes the oracle is too slow to run in full; check
+    size-independent properties instead: SAG(ones) == degree exactly (the reference's own
+    verification, unitest.py:54-63), linearity, GCN closed form on sampled rows, and agreement with
+    the multi-threaded oracle on the whole output."""
+    gr = graph.lookalike(name, device=DEV, scale=scale)
+    rp, ci, n = gr["row_ptr"], gr["col_idx"], gr["num_nodes"]
+    pp, pn = ops.build_part(32, rp)
+    deg = ops.degrees_from_row_ptr(rp)
+    ones = torch.ones(n, dim, device=DEV)
+    out = ops.SAG(ones, rp, ci, deg, pp, pn, 32, 32, 8)
+    want = (rp[1:] - rp[:-1]).float()[:, None].expand(n, dim)
+    assert torch.equal(out, want)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    A = torch.randn(n, dim, device=DEV, generator=gen)
+    B = torch.randn(n, dim, device=DEV, generator=gen)
+    sa, sb = ops.SAG(A, rp, ci, deg, pp, pn, 32, 32, 8), ops.SAG(B, rp, ci, deg, pp, pn, 32, 32, 8)
+    sab = ops.SAG(A + 2 * B, rp, ci, deg, pp, pn, 32, 32, 8)
+    lin = sa + 2 * sb
+    assert ((sab - lin).abs().max() / lin.abs().max()).item() < 1e-5
+    # whole output against the multi-threaded oracle
+    got = ops.forward(A, torch.eye(dim, device=DEV), rp, ci, deg, pp, pn, 32, 32, 8)[0].cpu().numpy()
+    ref = oracle.aggregate(1, A.cpu().numpy(), ci.cpu().numpy(), deg.cpu().numpy(), 1.0,
+                           pp.cpu().numpy(), pn.cpu().numpy(), threads=-1)
+    assert_close(got, ref, what=name)
