@@ -1,0 +1,176 @@
+"""Multi-GPU sharding of the aggregation path: 1-D vertex-range partition + halo exchange.
+
+The reference is single-GPU (no NCCL/MPI call site anywhere); this is new functionality
+asked for by BASELINE.json's north_star ("graphs ... 1-D vertex-range partitioned across the 8xB200
+box with a single NCCL all-to-all of halo neighbor features per layer over NVLink").
+
+Layout (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU tests):
+  * rank r owns the contiguous vertex range [v_r, v_{r+1}), cut so every rank holds ~E/world edges
+    (balanced by edge count, not node count: the graphs are skewed);
+  * it keeps the CSR rows of its range with column ids remapped to a LOCAL index space
+    [0, n_local) = own rows, [n_local, n_local + n_halo) = halo = sorted unique remote neighbours
+    (sorted by global id => automatically grouped by owner, ranges being contiguous);
+  * features live in ONE buffer X_ext [n_local + n_halo, D]; the first n_local rows are the rank's own
+    features (a view, no copy), the halo rows are filled by `exchange()`: each owner gathers the rows
+    its peers asked for (index lists swapped once at setup) and ONE all_to_all_single moves them;
+    every remote row crosses NVLink once per aggregation no matter how many local edges use it;
+  * the aggregation kernel then runs unchanged on the local CSR over X_ext.  F4 (the backward reuses the
+    same CSR) means forward and backward need exactly the same exchange, no transpose.
+  * `degrees` of the halo nodes are fetched once at setup with the same exchange.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+
+def partition_ranges(row_ptr, world):
+    """Vertex boundaries v[0..world] with ~equal edge counts: v_g = first row whose offset >= g*E/world."""
+    rp = row_ptr.to(torch.int64)
+    n = rp.numel() - 1
+    E = int(rp[-1])
+    targets = torch.tensor([(E * g) // world for g in range(world + 1)], dtype=torch.int64, device=rp.device)
+    v = torch.searchsorted(rp, targets, right=False).clamp_(0, n)
+    v[0], v[-1] = 0, n
+    v = torch.cummax(v, 0).values
+    return [int(x) for x in v.cpu()]
+
+
+def _a2a(out, inp, out_splits, in_splits, group):
+    """all_to_all_single, or point-to-point exchanges on backends without it (gloo)."""
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=group)
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ooff = [0]
+    ioff = [0]
+    for s in out_splits:
+        ooff.append(ooff[-1] + s)
+    for s in in_splits:
+        ioff.append(ioff[-1] + s)
+    reqs = []
+    for p in range(world):
+        if p == rank:
+            out[ooff[p]:ooff[p + 1]].copy_(inp[ioff[p]:ioff[p + 1]])
+            continue
+        if in_splits[p]:
+            reqs.append(dist.isend(inp[ioff[p]:ioff[p + 1]].contiguous(), dist.get_global_rank(group, p) if group else p, group=group))
+        if out_splits[p]:
+            reqs.append(dist.irecv(out[ooff[p]:ooff[p + 1]], dist.get_global_rank(group, p) if group else p, group=group))
+    for r in reqs:
+        r.wait()
+
+
+class ShardedGraph:
+    """This rank's shard of a graph every rank can see (replicated CSR in, sharded tables out)."""
+
+    def __init__(self, row_ptr, col_idx, part_size, device=None, group=None, ranges=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        device = torch.device(device) if device is not None else row_ptr.device
+        self.device = device
+        self.part_size = int(part_size)
+        self.ranges = ranges if ranges is not None else partition_ranges(row_ptr, self.world)
+        v0, v1 = self.ranges[self.rank], self.ranges[self.rank + 1]
+        self.v0, self.n_local = v0, v1 - v0
+        self.num_nodes_global = row_ptr.numel() - 1
+        e0, e1 = int(row_ptr[v0]), int(row_ptr[v1])
+        self.num_edges_local = e1 - e0
+        self.num_edges_global = int(row_ptr[-1])
+        rp_local = (row_ptr[v0:v1 + 1].to(torch.int64) - e0).to(torch.int32).to(device)
+        cols = col_idx[e0:e1].to(device).to(torch.int64)
+        bounds = torch.tensor(self.ranges, dtype=torch.int64, device=device)
+        remote = (cols < v0) | (cols >= v1)
+        halo = torch.unique(cols[remote])                                   # sorted => grouped by owner
+        self.n_halo = int(halo.numel())
+        self.halo_ids = halo
+        owner = torch.searchsorted(bounds, halo, right=True) - 1
+        self.recv_counts = [int(x) for x in torch.bincount(owner, minlength=self.world).cpu()]
+        local_cols = torch.where(remote, self.n_local + torch.searchsorted(halo, cols), cols - v0)
+        self.row_ptr = rp_local.contiguous()
+        self.col_idx = local_cols.to(torch.int32).contiguous()
+        # tell every owner which of ITS rows we need (as row indices local to the owner)
+        want = (halo - bounds[owner]).to(torch.int64)
+        rc = torch.tensor(self.recv_counts, dtype=torch.int64, device=device)
+        sc = torch.empty_like(rc)
+        _a2a(sc, rc, [1] * self.world, [1] * self.world, group)
+        self.send_counts = [int(x) for x in sc.cpu()]
+        self.send_idx = torch.empty(sum(self.send_counts), dtype=torch.int64, device=device)
+        _a2a(self.send_idx, want, self.send_counts, self.recv_counts, group)
+        self.n_ext = self.n_local + self.n_halo
+        self._tables_built = False
+        self.part_ptr = self.part2node = self.degrees_ext = None
+
+    # -------------------------------------------------------------------------------- setup on the device
+    def build_tables(self, degrees_global=None):
+        """Neighbour-group table of the local CSR (device build_part) and degrees of local + halo nodes.
+        The GCN degree is the GLOBAL row degree, which a rank knows for its own rows; halo degrees come
+        through the exchange."""
+        from . import ops
+        if self.device.type == "cuda":
+            self.part_ptr, self.part2node = ops.build_part_exact(self.part_size, self.row_ptr)
+            deg_local = ops.degrees_from_row_ptr(self.row_ptr)
+        else:   # CPU (gloo tests): host build_part of the C ABI + torch ops for the degrees
+            self.part_ptr, self.part2node = ops.build_part_exact(self.part_size, self.row_ptr)
+            d = (self.row_ptr[1:] - self.row_ptr[:-1]).to(torch.float32)
+            deg_local = torch.sqrt(torch.clamp(d, min=1.0))
+        ext = torch.empty(self.n_ext, 1, dtype=torch.float32, device=self.device)
+        ext[:self.n_local, 0] = deg_local
+        self.exchange(ext)
+        self.degrees_ext = ext[:, 0].contiguous()
+        self._tables_built = True
+        return self
+
+    def new_features(self, dim, dtype=torch.float32):
+        """X_ext [n_local + n_halo, dim]; fill [:n_local] (= .local(x)) with this rank's rows."""
+        return torch.empty(self.n_ext, dim, dtype=dtype, device=self.device)
+
+    def local(self, x_ext):
+        return x_ext[:self.n_local]
+
+    # -------------------------------------------------------------------------------- per aggregation
+    def exchange(self, x_ext):
+        """Fill the halo rows of x_ext from their owners: gather + ONE all-to-all."""
+        if self.world == 1:
+            return x_ext
+        send = x_ext[:self.n_local].index_select(0, self.send_idx)
+        _a2a(x_ext[self.n_local:], send, self.recv_counts, self.send_counts, self.group)
+        return x_ext
+
+    def halo_bytes(self, dim, elem=4):
+        return {"recv": self.n_halo * dim * elem, "send": int(self.send_idx.numel()) * dim * elem}
+
+    def aggregate(self, mode, x_ext, out=None, eps=0.5, dim_worker=32, warp_per_block=8, do_exchange=True):
+        """out[n_local, D] = aggregation of this rank's rows (mode 0 SAG, 1 GCN, 2 GIN) over X_ext."""
+        from . import _lib
+        assert self._tables_built, "call build_tables() first"
+        if do_exchange:
+            self.exchange(x_ext)
+        d = x_ext.shape[1]
+        if out is None:
+            out = torch.empty(self.n_local, d, dtype=torch.float32, device=self.device)
+        lib = _lib.load()
+        p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = self.part2node.numel()
+        tune = (self.part_size, int(dim_worker), int(warp_per_block), st)
+        if mode == 1:
+            rc = lib.gnna_gcn_aggregate_f32(p(x_ext), p(out), p(self.row_ptr), p(self.col_idx), p(self.degrees_ext),
+                                            p(self.part_ptr), p(self.part2node), self.n_local, d, P, *tune)
+        elif mode == 2:
+            rc = lib.gnna_gin_aggregate_f32(p(x_ext), p(out), p(self.row_ptr), p(self.col_idx), float(eps),
+                                            p(self.part_ptr), p(self.part2node), self.n_local, d, P, *tune)
+        else:
+            rc = lib.gnna_sag_f32(p(x_ext), p(out), p(self.row_ptr), p(self.col_idx),
+                                  p(self.part_ptr), p(self.part2node), self.n_local, d, P, *tune)
+        _lib.check(rc, "sharded aggregate")
+        return out
+
+
+def allreduce_weight_grad(d_weight, group=None):
+    """dW = X^T G is a sum over rows => sum over ranks (tiny: din x dout)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(d_weight, group=group)
+    return d_weight

@@ -10,13 +10,20 @@ from gnnadvisor_osdi21_b200 import graph
 RTOL = 1e-4
 
 
-def assert_close(got, ref, rtol=RTOL, what=""):
+def assert_close(got, ref, rtol=RTOL, what="", terms=None):
+    """|got - ref| <= rtol * scale, scale = max(|ref|, 1e-3*||ref||_inf).
+    `terms` (optional, same shape): the sum of the ABSOLUTE values of the terms each output element
+    adds up (e.g. |G| @ |W^T| for dX = G @ W^T).  Where an element is the result of cancellation
+    (|ref| << terms) the summation order -- which neither the reference's atomics nor cuBLAS fix --
+    decides more than rtol*|ref|; the error is then bounded relative to the terms instead."""
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     if ref.size == 0:
         return
     scale = np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())
+    if terms is not None:
+        scale = np.maximum(scale, 0.1 * np.asarray(terms, dtype=np.float64))
     scale = np.maximum(scale, 1e-30)
     err = np.abs(got - ref) / scale
     assert np.isfinite(got).all(), what + ": non-finite output"
@@ -37,3 +44,14 @@ def rand_features(n, d, seed):
 def rand_weight(din, dout, seed):
     g = torch.Generator().manual_seed(seed)
     return ((torch.rand(din, dout, generator=g) * 2 - 1) / np.sqrt(dout)).numpy()
+
+
+def golden_terms(g, k, oracle):
+    """Absolute-term bounds (see assert_close) for the dense-product outputs of one golden case."""
+    f64 = np.float64
+    rp, ci = g[k + "row_ptr"], g[k + "col_idx"]
+    X, W, dO = np.abs(g[k + "X"]).astype(f64), np.abs(g[k + "W"]).astype(f64), np.abs(g[k + "dO"]).astype(f64)
+    aG = oracle.closed_form(1, dO, rp, ci)                       # sum of |terms| of G = Ahat @ dO
+    aS = np.abs(g[k + "forward_gin_agg"]).astype(f64)
+    return {"dX": aG @ W.T, "dW": X.T @ aG, "gin_out": oracle.closed_form(2, X, rp, ci, 0.5) @ W,
+            "gin_dX": oracle.closed_form(2, dO @ W.T, rp, ci, 0.5), "gin_dW": aS.T @ dO}

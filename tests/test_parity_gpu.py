@@ -11,7 +11,7 @@ import pytest
 import torch
 
 import oracle
-from helpers import assert_close, make_graph, rand_features, rand_weight
+from helpers import assert_close, golden_terms, make_graph, rand_features, rand_weight
 from gnnadvisor_osdi21_b200 import graph, ops, layers
 
 pytestmark = pytest.mark.gpu
@@ -128,16 +128,18 @@ def test_layer_operators_against_oracle():
         assert_close(out.cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], what="forward")
         dX, dW = ops.backward(dOd, dXd, dWd, *g.gargs(), g.d_deg, *g.pargs(), ps, 32, 8)
         odX, odW = oracle.backward(dO, X, W, rp, ci, g.deg, g.pp, g.pn)
-        assert_close(dX.cpu().numpy(), odX, what="backward dX")
-        assert_close(dW.cpu().numpy(), odW, what="backward dW")
+        aG = np.abs(oracle.aggregate(1, dO, ci, g.deg, 1.0, g.pp, g.pn)).astype(np.float64)
+        assert_close(dX.cpu().numpy(), odX, what="backward dX", terms=aG @ np.abs(W.T))
+        assert_close(dW.cpu().numpy(), odW, what="backward dW", terms=np.abs(X.T).astype(np.float64) @ aG)
         o, S = ops.forward_gin(dXd, dWd, *g.gargs(), 0.5, *g.pargs(), ps, 32, 2)
         oo, oS = oracle.forward_gin(X, W, rp, ci, 0.5, g.pp, g.pn)
         assert_close(S.cpu().numpy(), oS, what="gin agg")
         assert_close(o.cpu().numpy(), oo, what="gin out")
         dXg, dWg = ops.backward_gin(dOd, S, dWd, *g.gargs(), 0.5, *g.pargs(), ps, 32, 2)
         odXg, odWg = oracle.backward_gin(dO, oS, W, rp, ci, 0.5, g.pp, g.pn)
-        assert_close(dXg.cpu().numpy(), odXg, what="gin dX")
-        assert_close(dWg.cpu().numpy(), odWg, what="gin dW")
+        aPm = np.abs(dO).astype(np.float64) @ np.abs(W.T)
+        assert_close(dXg.cpu().numpy(), odXg, what="gin dX", terms=oracle.closed_form(2, aPm, rp, ci, 0.5))
+        assert_close(dWg.cpu().numpy(), odWg, what="gin dW", terms=np.abs(oS.T).astype(np.float64) @ np.abs(dO))
 
 
 def test_reference_cuda_golden(golden_dir):
@@ -157,14 +159,15 @@ def test_reference_cuda_golden(golden_dir):
         assert_close(ops.SAG(X, d_rp, d_ci, deg, pp, pn, ps, dw, wpb).cpu().numpy(), gz[k + "SAG"], what=k + "SAG")
         assert_close(ops.forward(X, W, d_rp, d_ci, deg, pp, pn, ps, dw, wpb)[0].cpu().numpy(), gz[k + "forward"], what=k + "forward")
         dX, dW = ops.backward(dO, X, W, d_rp, d_ci, deg, pp, pn, ps, dw, wpb)
-        assert_close(dX.cpu().numpy(), gz[k + "backward_dX"], what=k + "dX")
-        assert_close(dW.cpu().numpy(), gz[k + "backward_dW"], what=k + "dW")
+        t = golden_terms(gz, k, oracle)
+        assert_close(dX.cpu().numpy(), gz[k + "backward_dX"], what=k + "dX", terms=t["dX"])
+        assert_close(dW.cpu().numpy(), gz[k + "backward_dW"], what=k + "dW", terms=t["dW"])
         o, S = ops.forward_gin(X, W, d_rp, d_ci, 0.5, pp, pn, ps, dw, wpb)
         assert_close(S.cpu().numpy(), gz[k + "forward_gin_agg"], what=k + "gin agg")
-        assert_close(o.cpu().numpy(), gz[k + "forward_gin"], what=k + "gin out")
+        assert_close(o.cpu().numpy(), gz[k + "forward_gin"], what=k + "gin out", terms=t["gin_out"])
         dXg, dWg = ops.backward_gin(dO, dev(gz[k + "forward_gin_agg"]), W, d_rp, d_ci, 0.5, pp, pn, ps, dw, wpb)
-        assert_close(dXg.cpu().numpy(), gz[k + "backward_gin_dX"], what=k + "gin dX")
-        assert_close(dWg.cpu().numpy(), gz[k + "backward_gin_dW"], what=k + "gin dW")
+        assert_close(dXg.cpu().numpy(), gz[k + "backward_gin_dX"], what=k + "gin dX", terms=t["gin_dX"])
+        assert_close(dWg.cpu().numpy(), gz[k + "backward_gin_dW"], what=k + "gin dW", terms=t["gin_dW"])
 
 
 # ------------------------------------------------------------------------------------------ edge cases
