@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libgnna_b200.so")
+# GNNA_B200_LIB selects another build of the same library (tuning variants, tools/sweep_dims.py)
+LIB_PATH = os.environ.get("GNNA_B200_LIB") or os.path.join(_PKG, "libgnna_b200.so")
 
 c_i32p = ctypes.c_void_p
 c_f32p = ctypes.c_void_p
@@ -37,6 +38,8 @@ SIGNATURES = {
     "gnna_sag_f32": (i32, [c_f32p, c_f32p] + _GRAPH + _PARTS + [i64, i32, i64] + _TUNE),
     "gnna_gcn_aggregate_f32": (i32, [c_f32p, c_f32p] + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i64] + _TUNE),
     "gnna_gin_aggregate_f32": (i32, [c_f32p, c_f32p] + _GRAPH + [ctypes.c_float] + _PARTS + [i64, i32, i64] + _TUNE),
+    "gnna_aggregate_f32_ex": (i32, [i32, c_f32p, i64, c_f32p, i64] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
+                              + [i32, i64] + _TUNE),
     "gnna_aggregate_bf16": (i32, [i32, ctypes.c_void_p, c_f32p] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
                             + [i64, i32, i64] + _TUNE),
     "gnna_forward_f32": (i32, [c_f32p] * 4 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
@@ -45,8 +48,10 @@ SIGNATURES = {
                              + [i64, i32, i32, i64] + _TUNE),
     "gnna_backward_gin_f32": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, c_f32p] + _GRAPH + _PARTS
                               + [i64, i32, i32, i64] + _TUNE),
+    "gnna_rabbit_reorder_host": (i32, [c_i32p, c_i32p, i64, i64, c_i32p]),
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
     "gnna_launch_count": (i64, [i32]),
+    "gnna_set_gcn_exact": (i32, [i32]),
 }
 
 _lib = None
@@ -78,3 +83,8 @@ def check(rc, what):
 
 def launch_count(reset=False):
     return int(load().gnna_launch_count(1 if reset else 0))
+
+
+def set_gcn_exact(on):
+    """True: per-edge rounding of the reference (bit-identical single-group rows); False: pre-scaled (default)."""
+    return bool(load().gnna_set_gcn_exact(1 if on else 0))

@@ -27,6 +27,7 @@
 //   * 64-bit row offsets: num_nodes*dim may exceed 2^31 (the reference's PackedTensorAccessor32
 //     cannot).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -37,8 +38,14 @@
 #ifndef GNNA_LB
 #define GNNA_LB 512
 #endif
+// Measured on B200 (tools/sweep_dims.py, profiles/r01_sweep_*): 3 CTAs (42 registers, 48 resident warps)
+// is 5-10 % faster than 2 for sub-warps of <= 16 lanes; full-warp rows (LPR = 32) and wide rows
+// (KCH >= 2) are best with the 64-register budget.
 #ifndef GNNA_MIN_CTAS
-#define GNNA_MIN_CTAS 2
+#define GNNA_MIN_CTAS 3
+#endif
+#ifndef GNNA_WIDE_MIN_CTAS
+#define GNNA_WIDE_MIN_CTAS 2
 #endif
 
 namespace gnna {
@@ -79,6 +86,26 @@ __device__ __forceinline__ void ldg_raw(Raw<2> &r, const void *p, bool ok) {
                  "mov.b16 %0, 0;\n\t"
                  "@p ld.global.nc.b16 %0, [%1];\n\t}"
                  : "=h"(r.v) : "l"(p), "r"((int)ok));
+}
+
+// unpredicated variants (fast path: whole batch valid) -- still volatile asm so they stay batched
+__device__ __forceinline__ void ldg_raw(Raw<16> &r, const void *p) {
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.v.x), "=r"(r.v.y), "=r"(r.v.z), "=r"(r.v.w) : "l"(p));
+}
+__device__ __forceinline__ void ldg_raw(Raw<8> &r, const void *p) {
+    asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(r.v.x), "=r"(r.v.y) : "l"(p));
+}
+__device__ __forceinline__ void ldg_raw(Raw<4> &r, const void *p) {
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(r.v) : "l"(p));
+}
+__device__ __forceinline__ void ldg_raw(Raw<2> &r, const void *p) {
+    asm volatile("ld.global.nc.b16 %0, [%1];" : "=h"(r.v) : "l"(p));
+}
+// index streams (col_idx, group table) are read exactly once: keep them out of L1
+__device__ __forceinline__ int ldg_stream(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -132,6 +159,18 @@ __device__ __forceinline__ void store_or_red(float *p, const float (&a)[V], bool
     }
 }
 
+// output rows that are not 16-byte aligned (dim % 4 != 0): element-wise, bounded by the row end
+template <int V>
+__device__ __forceinline__ void store_or_red_scalar(float *p, const float (&a)[V], bool own, int valid) {
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+        if (i < valid) {
+            if (own) p[i] = a[i];
+            else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p + i), "f"(a[i]) : "memory");
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 //   T    element type of X (float / __nv_bfloat16); out is always fp32
@@ -140,20 +179,72 @@ __device__ __forceinline__ void store_or_red(float *p, const float (&a)[V], bool
 //   KCH  vector chunks per lane inside one d-tile (d-tile = LPR*KCH*VEC elements)
 //   WEIGHTED  GCN: per-neighbour weight fl(deg[src]*deg[nid])
 // ------------------------------------------------------------------------------------------
+// base + (int64)a * b as ONE IMAD.WIDE (the compiler emits IMAD.WIDE + a 64-bit add otherwise)
+__device__ __forceinline__ const char *mad_wide(int a, int b, const char *base) {
+    const char *r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(base));
+    return r;
+}
+
+// flags of aggregate_kernel
+enum : int {
+    F_SCALE = 1,      // multiply the group sum by `scale` before the merge (GIN: eps, kernel.cu:686)
+    F_ROWSCALE = 2,   // multiply the group sum by degrees[src] (GCN on pre-scaled features, see prescale_rows)
+    F_OUT_SCALAR = 8, // out rows are not 16-byte aligned (dim % VEC != 0; X was re-packed to ldx = round_up(dim, VEC))
+};
+
+// One batch step: U neighbour rows of this sub-warp are loaded (all loads issued first), then summed in
+// neighbour order.  PRED=false is the fast path (whole warp has U more neighbours, all chunks in range).
+template <typename T, int VEC, int LPR, int KCH, int U, int IPL, bool WEIGHTED, bool PRED>
+__device__ __forceinline__ void batch_step(const char *const (&lane_base)[KCH], int row_bytes, int nchunks, int chunk0, int j0,
+                                           const int (&nid)[IPL], const float (&wgt)[IPL], float (&acc)[KCH][VEC])
+{
+    using RawT = Raw<VEC * (int)sizeof(T)>;
+    constexpr unsigned FULL = 0xffffffffu;
+    RawT raw[U][KCH];
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int j = j0 + u;                        // compile-time after unrolling
+        const int nj = __shfl_sync(FULL, nid[j / LPR], j % LPR, LPR);
+        if (WEIGHTED) w[u] = __shfl_sync(FULL, wgt[j / LPR], j % LPR, LPR);
+#pragma unroll
+        for (int k = 0; k < KCH; k++) {
+            // one IMAD.WIDE per load: lane_base[k] (64-bit, this lane's chunk inside row 0) + nj * row_bytes
+            const char *p = mad_wide(nj, row_bytes, lane_base[k]);
+            if (PRED) ldg_raw(raw[u][k], p, nj >= 0);
+            else ldg_raw(raw[u][k], p);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+        for (int k = 0; k < KCH; k++) {
+            float f[VEC];
+            unpack(raw[u][k], f, T());
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                if (WEIGHTED) acc[k][v] = __fadd_rn(acc[k][v], __fmul_rn(w[u], f[v]));
+                else acc[k][v] = __fadd_rn(acc[k][v], f[v]);
+            }
+        }
+    }
+}
+
 template <typename T, int VEC, int LPR, int KCH, bool WEIGHTED>
-__global__ void __launch_bounds__(GNNA_LB, GNNA_MIN_CTAS)
+__global__ void __launch_bounds__(GNNA_LB, (KCH >= 2 || LPR == 32) ? GNNA_WIDE_MIN_CTAS : GNNA_MIN_CTAS)
 aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
                  const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                  const float *__restrict__ degrees,
                  const int32_t *__restrict__ part_ptr, const int32_t *__restrict__ part2node,
-                 long long num_parts, int dim, float scale, int apply_scale)
+                 long long num_parts, int dim, int ldx, float scale, int flags)
 {
+    // dim = logical row width = row stride of `out`; ldx = row stride of X in elements (>= dim, % VEC == 0)
     constexpr int S = 32 / LPR;                      // neighbour-groups per warp
     constexpr int IPL = (LPR >= 8) ? 1 : 8 / LPR;    // neighbour ids fetched per lane per batch
     constexpr int B = LPR * IPL;                     // neighbours per batch (>= 8)
     constexpr int U = (KCH >= 8) ? 1 : 8 / KCH;      // neighbour rows in flight per sub-warp
     static_assert(B % U == 0, "batch must be a multiple of the unroll");
-    using RawT = Raw<VEC * (int)sizeof(T)>;
     constexpr unsigned FULL = 0xffffffffu;
 
     const int lane = threadIdx.x & 31;
@@ -161,31 +252,40 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
     const int l = lane % LPR;
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long g = warp_global * S + sub;
-    const int nchunks = dim / VEC;
+    const int nchunks = ldx / VEC;
     const int chunk0 = blockIdx.y * (LPR * KCH) + l;   // this lane's first chunk; then += LPR
 
     const bool gvalid = g < num_parts;
     int src = 0, beg = 0, end = 0;
     if (gvalid) {
-        src = __ldg(part2node + g);
-        beg = __ldg(part_ptr + g);
-        end = __ldg(part_ptr + g + 1);
+        src = ldg_stream(part2node + g);
+        beg = ldg_stream(part_ptr + g);
+        end = ldg_stream(part_ptr + g + 1);
     }
     const int len = max(end - beg, 0);               // end <= beg: empty group, contributes nothing
     const int maxlen = __reduce_max_sync(FULL, len); // warp-uniform trip count
     if (maxlen == 0) return;
+    // neighbours every sub-warp of this warp still has: batches below this bound need no predicates
+    const int minlen = __reduce_min_sync(FULL, len);
 
     float src_norm = 0.f;
     if (WEIGHTED && gvalid) src_norm = __ldg(degrees + src);
 
     float acc[KCH][VEC];
+    const char *lane_base[KCH];
+    const int row_bytes = ldx * (int)sizeof(T);
 #pragma unroll
-    for (int k = 0; k < KCH; k++)
+    for (int k = 0; k < KCH; k++) {
+        // a lane whose chunk lies beyond the row end reads chunk 0 instead (same cache line as lane 0, no
+        // extra traffic): its sums are never stored, and the fast path below needs no per-lane predicate
+        const int c = chunk0 + k * LPR;
+        lane_base[k] = reinterpret_cast<const char *>(X) + (size_t)(c < nchunks ? c : 0) * (VEC * sizeof(T));
 #pragma unroll
         for (int v = 0; v < VEC; v++) acc[k][v] = 0.f;
+    }
 
     for (int base = 0; base < maxlen; base += B) {
-        // cooperative, coalesced fetch of this batch's neighbour ids (+ GCN weights)
+        // cooperative, coalesced fetch of this batch's neighbour ids (+ GCN weights in exact mode)
         int nid[IPL];
         float wgt[IPL];
 #pragma unroll
@@ -194,40 +294,20 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
             nid[i] = -1;
             wgt[i] = 0.f;
             if (n < len) {
-                nid[i] = __ldg(col_idx + beg + n);
+                nid[i] = ldg_stream(col_idx + beg + n);
                 if (WEIGHTED) wgt[i] = __fmul_rn(src_norm, __ldg(degrees + nid[i]));
             }
         }
-        const int cnt = min(B, maxlen - base);       // warp-uniform
+        if (base + B <= minlen) {
 #pragma unroll
-        for (int j0 = 0; j0 < B; j0 += U) {
-            if (j0 >= cnt) break;
-            RawT raw[U][KCH];
-            float w[U];
+            for (int j0 = 0; j0 < B; j0 += U)
+                batch_step<T, VEC, LPR, KCH, U, IPL, WEIGHTED, false>(lane_base, row_bytes, nchunks, chunk0, j0, nid, wgt, acc);
+        } else {
+            const int cnt = min(B, maxlen - base);   // warp-uniform
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int j = j0 + u;                // compile-time after unrolling
-                const int nj = __shfl_sync(FULL, nid[j / LPR], j % LPR, LPR);
-                if (WEIGHTED) w[u] = __shfl_sync(FULL, wgt[j / LPR], j % LPR, LPR);
-                const T *row = X + (long long)nj * dim;
-#pragma unroll
-                for (int k = 0; k < KCH; k++) {
-                    const int c = chunk0 + k * LPR;
-                    ldg_raw(raw[u][k], row + (long long)c * VEC, nj >= 0 && c < nchunks);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-#pragma unroll
-                for (int k = 0; k < KCH; k++) {
-                    float f[VEC];
-                    unpack(raw[u][k], f, T());
-#pragma unroll
-                    for (int v = 0; v < VEC; v++) {
-                        if (WEIGHTED) acc[k][v] = __fadd_rn(acc[k][v], __fmul_rn(w[u], f[v]));
-                        else acc[k][v] = __fadd_rn(acc[k][v], f[v]);
-                    }
-                }
+            for (int j0 = 0; j0 < B; j0 += U) {
+                if (j0 >= cnt) break;
+                batch_step<T, VEC, LPR, KCH, U, IPL, WEIGHTED, true>(lane_base, row_bytes, nchunks, chunk0, j0, nid, wgt, acc);
             }
         }
     }
@@ -235,17 +315,54 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
     if (len > 0) {
         // plain store when this group is the node's whole adjacency list, else vector reduction
         const bool own = (beg == __ldg(row_ptr + src)) && (end == __ldg(row_ptr + src + 1));
+        float mul = (flags & F_SCALE) ? scale : 1.f;
+        if (flags & F_ROWSCALE) mul = __ldg(degrees + src);
         float *orow = out + (long long)src * dim;
 #pragma unroll
         for (int k = 0; k < KCH; k++) {
             const int c = chunk0 + k * LPR;
             if (c < nchunks) {
-                if (apply_scale) {
+                if (flags & (F_SCALE | F_ROWSCALE)) {
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) acc[k][v] = __fmul_rn(scale, acc[k][v]);
+                    for (int v = 0; v < VEC; v++) acc[k][v] = __fmul_rn(mul, acc[k][v]);
                 }
-                store_or_red<VEC>(orow + (long long)c * VEC, acc[k], own);
+                if (flags & F_OUT_SCALAR) store_or_red_scalar<VEC>(orow + (long long)c * VEC, acc[k], own, dim - c * VEC);
+                else store_or_red<VEC>(orow + (long long)c * VEC, acc[k], own);
             }
+        }
+    }
+}
+
+// Xs[i, 0:dim] = (degrees ? degrees[i] : 1) * X[i, 0:dim], Xs[i, dim:ldx] = 0.
+// The pre-pass of the aggregation: GCN pre-scale and/or re-pack of rows whose width is not a multiple
+// of four floats to a 16-byte aligned stride (so the gather can use 128-bit loads).  N*dim elements,
+// i.e. 2N/E of the gather traffic.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+repack_rows_kernel(const float *__restrict__ X, float *__restrict__ Xs, const float *__restrict__ degrees,
+                   long long num_nodes, int dim, int ldx)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if constexpr (VEC == 4) {   // dim == ldx, both 16-byte aligned
+        const int cpr = dim / 4;
+        const long long total = num_nodes * cpr;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const float n = degrees ? __ldg(degrees + i / cpr) : 1.f;
+            float4 v = __ldg(reinterpret_cast<const float4 *>(X) + i);
+            v.x = __fmul_rn(n, v.x); v.y = __fmul_rn(n, v.y); v.z = __fmul_rn(n, v.z); v.w = __fmul_rn(n, v.w);
+            reinterpret_cast<float4 *>(Xs)[i] = v;
+        }
+    } else {
+        const long long total = num_nodes * ldx;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const long long r = i / ldx;
+            const int c = (int)(i - r * ldx);
+            float v = 0.f;
+            if (c < dim) {
+                v = __ldg(X + r * dim + c);
+                if (degrees) v = __fmul_rn(__ldg(degrees + r), v);
+            }
+            Xs[i] = v;
         }
     }
 }
@@ -265,11 +382,15 @@ struct Geometry {
 // but is rounded down to a power of two and never exceeds what the row needs; the lanes the
 // reference would leave idle work on other groups.  dim_worker <= 0: as many lanes as the row has
 // 16-byte chunks (one chunk per lane), i.e. fully coalesced 128-bit loads.
+// `dim` here is the row stride the kernel loads with (ldx): fp32 rows are always re-packed to a
+// multiple of four floats first, so fp32 uses 128-bit loads only; bf16 rows pick the widest vector
+// that divides them.
 static Geometry choose_geometry(int elem_bytes, int dim, long long num_parts, int dim_worker, int warp_per_block)
 {
     Geometry g;
     const int maxvec = 16 / elem_bytes;
     g.vec = maxvec;
+    if (elem_bytes == 4 && dim % 4 != 0) dim = (dim + 7) / 8 * 8;
     while (g.vec > 1 && dim % g.vec != 0) g.vec /= 2;
     const int nchunks = dim / g.vec;
     const int need = pow2_ceil(nchunks) > 32 ? 32 : pow2_ceil(nchunks);
@@ -293,11 +414,11 @@ static Geometry choose_geometry(int elem_bytes, int dim, long long num_parts, in
 template <typename T, int VEC, int LPR, int KCH, bool W>
 static cudaError_t launch(const Geometry &g, cudaStream_t st, const void *X, float *out, const int32_t *row_ptr,
                           const int32_t *col_idx, const float *deg, const int32_t *pp, const int32_t *pn,
-                          long long P, int dim, float scale, int apply_scale)
+                          long long P, int dim, int ldx, float scale, int flags)
 {
     dim3 grid((unsigned)g.gx, (unsigned)g.gy, 1), block(g.wpb * 32, 1, 1);
     aggregate_kernel<T, VEC, LPR, KCH, W><<<grid, block, 0, st>>>(reinterpret_cast<const T *>(X), out, row_ptr, col_idx,
-                                                                  deg, pp, pn, P, dim, scale, apply_scale);
+                                                                  deg, pp, pn, P, dim, ldx, scale, flags);
     return cudaGetLastError();
 }
 
@@ -338,53 +459,147 @@ static cudaError_t dispatch_vec(const Geometry &g, A... a)
     return dispatch_lpr<T, 1, W>(g, a...);
 }
 
+// GCN rounding mode.  The reference computes fl(fl(n_i*n_j) * t_j) per edge, which costs one scattered
+// 4-byte gather of degrees[nid] per edge -- measured on B200 that gather is 1/3 of the kernel's L1TEX
+// wavefronts (profiles/r01_v1_*).  The default path therefore uses the algebraically identical
+//     out_i = n_i * sum_j (n_j * t_j)
+// i.e. one pre-scale pass over the [N, D] features (0.4 % of the gather traffic) and a weight-free
+// gather; each term differs from the reference's by at most 2 roundings (~1.2e-7 relative, well
+// inside the 1e-4 parity bar).  GNNA_GCN_EXACT=1 selects the reference's per-edge rounding.
+static int g_gcn_exact = -1;   // -1: not decided yet (environment), 0/1: set
+bool gcn_exact_mode()
+{
+    if (g_gcn_exact < 0) {
+        const char *e = getenv("GNNA_GCN_EXACT");
+        g_gcn_exact = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_gcn_exact == 1;
+}
+
+// Xs[i, 0:dim] = (degrees ? degrees[i] : 1) * X[i, 0:dim]; columns dim..ldx-1 zero.  X == Xs allowed when ldx == dim.
+int repack_rows(const float *X, float *Xs, const float *degrees, int64_t num_nodes, int dim, int ldx, cudaStream_t stream)
+{
+    if (num_nodes == 0 || dim == 0) return GNNA_OK;
+    const bool v4 = (ldx == dim) && (dim % 4 == 0) && ((((uintptr_t)X | (uintptr_t)Xs) & 15) == 0);
+    const long long items = v4 ? (long long)num_nodes * (dim / 4) : (long long)num_nodes * ldx;
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (v4) repack_rows_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(X, Xs, degrees, num_nodes, dim, ldx);
+    else repack_rows_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(X, Xs, degrees, num_nodes, dim, ldx);
+    GNNA_CUDA_CHECK(cudaGetLastError());
+    count_launch(1);
+    return GNNA_OK;
+}
+
+int prescale_rows(const float *X, float *Xs, const float *degrees, int64_t num_nodes, int dim, cudaStream_t stream)
+{
+    return repack_rows(X, Xs, degrees, num_nodes, dim, dim, stream);
+}
+
+// stream-ordered scratch: keep freed blocks in the pool instead of returning them to the OS at every sync
+static int scratch_alloc(float **p, size_t bytes, cudaStream_t stream)
+{
+    static bool pool_ready = false;
+    if (!pool_ready) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready = true;
+    }
+    GNNA_CUDA_CHECK(cudaMallocAsync((void **)p, bytes, stream));
+    return GNNA_OK;
+}
+
+// mode: MODE_SAG / MODE_GCN / MODE_GIN, or MODE_GCN_PRESCALED (X already holds n_j * t_j)
+// ldx: row stride of X in elements (0 = dim).
 int aggregate(int mode, int elem_bytes, const void *X, void *out,
               const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
               const int32_t *part_ptr, const int32_t *part2node,
               int64_t num_nodes, int dim, int64_t num_parts,
-              int part_size, int dim_worker, int warp_per_block, cudaStream_t stream)
+              int part_size, int dim_worker, int warp_per_block, cudaStream_t stream, int ldx, int64_t num_rows_x)
 {
     (void)part_size;  // group length is read from part_ptr; any table with sorted groups works
-    GNNA_REQUIRE(mode >= MODE_SAG && mode <= MODE_GIN, "aggregate: bad mode %d", mode);
+    GNNA_REQUIRE(mode >= MODE_SAG && mode <= MODE_GCN_PRESCALED, "aggregate: bad mode %d", mode);
     GNNA_REQUIRE(elem_bytes == 4 || elem_bytes == 2, "aggregate: element size %d not supported", elem_bytes);
     GNNA_REQUIRE(num_nodes >= 0 && dim >= 0 && num_parts >= 0, "aggregate: negative size");
     if (num_nodes == 0 || dim == 0) return GNNA_OK;
     GNNA_REQUIRE(X && out, "aggregate: null feature pointer");
-    GNNA_REQUIRE(mode != MODE_GCN || degrees, "aggregate: GCN mode needs degrees");
+    const bool gcn = (mode == MODE_GCN || mode == MODE_GCN_PRESCALED);
+    GNNA_REQUIRE(!gcn || degrees, "aggregate: GCN mode needs degrees");
+    if (ldx <= 0) ldx = dim;
+    if (num_rows_x <= 0) num_rows_x = num_nodes;     // rows of X (>= num_nodes when X carries halo rows)
+    GNNA_REQUIRE(ldx >= dim, "aggregate: ldx %d < dim %d", ldx, dim);
 
     // rows shared by several groups are merged with reductions, rows without neighbours stay zero
     GNNA_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)num_nodes * (size_t)dim, stream));
     if (num_parts == 0) return GNNA_OK;
     GNNA_REQUIRE(row_ptr && col_idx && part_ptr && part2node, "aggregate: null index pointer");
 
-    const Geometry g = choose_geometry(elem_bytes, dim, num_parts, dim_worker, warp_per_block);
-    GNNA_REQUIRE(g.gx <= 0x7fffffffLL, "aggregate: too many neighbour groups for one launch (%lld CTAs)", g.gx);
-    GNNA_REQUIRE(g.gy <= 65535, "aggregate: dim %d needs %d d-tiles (> 65535)", dim, g.gy);
+    // fp32 pre-pass into a stream-ordered scratch buffer when it pays:
+    //   * default GCN rounding: pre-scale rows by degrees (no per-edge degree gather afterwards)
+    //   * rows not 16-byte aligned (ldx % 4 != 0): re-pack to a stride that is, so the gather uses LDG.128
+    float *scratch = nullptr;
+    if (elem_bytes == 4) {
+        const bool want_scale = (mode == MODE_GCN && !gcn_exact_mode());
+        const bool want_pad = (ldx % 4 != 0) || ((uintptr_t)X & 15);
+        if (want_scale || want_pad) {
+            // whole 32-byte sectors per row when re-packing anyway (a 44-float row would straddle sectors)
+            const int new_ld = (dim % 4 == 0) ? dim : (dim + 7) / 8 * 8;
+            int rc = scratch_alloc(&scratch, sizeof(float) * (size_t)num_rows_x * (size_t)new_ld, stream);
+            if (rc != GNNA_OK) return rc;
+            rc = repack_rows((const float *)X, scratch, want_scale ? degrees : nullptr, num_rows_x, dim, new_ld, stream);
+            if (rc != GNNA_OK) { cudaFreeAsync(scratch, stream); return rc; }
+            X = scratch;
+            ldx = new_ld;
+            if (want_scale) mode = MODE_GCN_PRESCALED;
+        }
+    }
+
+    const Geometry g = choose_geometry(elem_bytes, ldx, num_parts, dim_worker, warp_per_block);
+    if (g.gx > 0x7fffffffLL || g.gy > 65535) {
+        if (scratch) cudaFreeAsync(scratch, stream);
+        return fail(GNNA_ERR_INVALID, "aggregate: launch too large (%lld x %d CTAs)", g.gx, g.gy);
+    }
     const float scale = (mode == MODE_GIN) ? eps : 1.0f;
-    const int apply_scale = (mode == MODE_GIN) ? 1 : 0;
+    int flags = 0;
+    if (mode == MODE_GIN) flags |= F_SCALE;
+    if (mode == MODE_GCN_PRESCALED) flags |= F_ROWSCALE;
+    if (dim % g.vec != 0 || (elem_bytes == 4 && (((uintptr_t)out & 15) || dim % 4 != 0))) flags |= F_OUT_SCALAR;
+    const bool weighted = (mode == MODE_GCN);
     float *o = reinterpret_cast<float *>(out);
     cudaError_t e;
     if (elem_bytes == 4) {
-        if (mode == MODE_GCN)
-            e = dispatch_vec<float, true>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                          (long long)num_parts, dim, scale, apply_scale);
+        if (weighted)
+            e = dispatch_lpr<float, 4, true>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
+                                             (long long)num_parts, dim, ldx, scale, flags);
         else
-            e = dispatch_vec<float, false>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                           (long long)num_parts, dim, scale, apply_scale);
+            e = dispatch_lpr<float, 4, false>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
+                                              (long long)num_parts, dim, ldx, scale, flags);
     } else {
-        if (mode == MODE_GCN)
+        if (weighted)
             e = dispatch_vec<__nv_bfloat16, true>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                                  (long long)num_parts, dim, scale, apply_scale);
+                                                  (long long)num_parts, dim, ldx, scale, flags);
         else
             e = dispatch_vec<__nv_bfloat16, false>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                                   (long long)num_parts, dim, scale, apply_scale);
+                                                   (long long)num_parts, dim, ldx, scale, flags);
     }
+    if (scratch) cudaFreeAsync(scratch, stream);
     if (e != cudaSuccess) return fail(GNNA_ERR_CUDA, "aggregate launch: %s", cudaGetErrorString(e));
     count_launch(1);
     return GNNA_OK;
 }
 
 }  // namespace gnna
+
+extern "C" int gnna_set_gcn_exact(int on)
+{
+    const int prev = gnna::gcn_exact_mode() ? 1 : 0;
+    gnna::g_gcn_exact = on ? 1 : 0;
+    return prev;
+}
 
 extern "C" int gnna_query_launch(int elem_bytes, int dim, int64_t num_parts, int dim_worker, int warp_per_block,
                                  gnna_launch_info *info)

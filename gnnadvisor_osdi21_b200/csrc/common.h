@@ -26,13 +26,19 @@ void count_launch(int n = 1);               // thread-local launch counter
         if (!(cond)) return ::gnna::fail(GNNA_ERR_INVALID, __VA_ARGS__); \
     } while (0)
 
-enum Mode { MODE_SAG = 0, MODE_GCN = 1, MODE_GIN = 2 };
+enum Mode { MODE_SAG = 0, MODE_GCN = 1, MODE_GIN = 2, MODE_GCN_PRESCALED = 3 };
 
 // One aggregation launch (aggregate.cu).  elem: 4 = fp32, 2 = bf16.
 int aggregate(int mode, int elem_bytes, const void *X, void *out,
               const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
               const int32_t *part_ptr, const int32_t *part2node,
               int64_t num_nodes, int dim, int64_t num_parts,
-              int part_size, int dim_worker, int warp_per_block, cudaStream_t stream);
+              int part_size, int dim_worker, int warp_per_block, cudaStream_t stream,
+              int ldx = 0, int64_t num_rows_x = 0);
+
+bool gcn_exact_mode();   // GNNA_GCN_EXACT / gnna_set_gcn_exact
+
+// Xs[i,:] = degrees[i] * X[i,:]  (X == Xs allowed)
+int prescale_rows(const float *X, float *Xs, const float *degrees, int64_t num_nodes, int dim, cudaStream_t stream);
 
 }  // namespace gnna

@@ -125,6 +125,17 @@ extern "C" int gnna_aggregate_bf16(int mode, const void *X_bf16, float *out_f32,
                      num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream);
 }
 
+extern "C" int gnna_aggregate_f32_ex(int mode, const float *X, int64_t num_src_rows, float *out, int64_t num_dst_rows,
+                                     const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
+                                     const int32_t *part_ptr, const int32_t *part2node, int dim, int64_t num_parts,
+                                     int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    GNNA_REQUIRE(mode >= MODE_SAG && mode <= MODE_GIN, "gnna_aggregate_f32_ex: bad mode %d", mode);
+    GNNA_REQUIRE(num_src_rows >= num_dst_rows, "gnna_aggregate_f32_ex: fewer source rows than destination rows");
+    return aggregate(mode, 4, X, out, row_ptr, col_idx, degrees, eps, part_ptr, part2node, num_dst_rows, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream, dim, num_src_rows);
+}
+
 #define GNNA_TRY(expr)             \
     do {                           \
         int _rc = (expr);          \
@@ -139,8 +150,14 @@ extern "C" int gnna_forward_f32(const float *X, const float *W, float *T_ws, flo
 {
     cudaStream_t st = (cudaStream_t)stream;
     GNNA_REQUIRE(X && W && T_ws && out, "gnna_forward_f32: null pointer");
+    GNNA_REQUIRE(degrees, "gnna_forward_f32: null degrees");
     GNNA_TRY(sgemm_rm(st, false, false, num_nodes, dout, din, X, W, T_ws));               // kernel.cu:280
-    return aggregate(MODE_GCN, 4, T_ws, out, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes, dout,
+    int mode = MODE_GCN;
+    if (!gcn_exact_mode()) {   // T is our own scratch: pre-scale it in place, no extra buffer
+        GNNA_TRY(prescale_rows(T_ws, T_ws, degrees, num_nodes, dout, st));
+        mode = MODE_GCN_PRESCALED;
+    }
+    return aggregate(mode, 4, T_ws, out, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes, dout,
                      num_parts, part_size, dim_worker, warp_per_block, st);               // kernel.cu:282-313
 }
 

@@ -155,16 +155,11 @@ class ShardedGraph:
         p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = self.part2node.numel()
-        tune = (self.part_size, int(dim_worker), int(warp_per_block), st)
-        if mode == 1:
-            rc = lib.gnna_gcn_aggregate_f32(p(x_ext), p(out), p(self.row_ptr), p(self.col_idx), p(self.degrees_ext),
-                                            p(self.part_ptr), p(self.part2node), self.n_local, d, P, *tune)
-        elif mode == 2:
-            rc = lib.gnna_gin_aggregate_f32(p(x_ext), p(out), p(self.row_ptr), p(self.col_idx), float(eps),
-                                            p(self.part_ptr), p(self.part2node), self.n_local, d, P, *tune)
-        else:
-            rc = lib.gnna_sag_f32(p(x_ext), p(out), p(self.row_ptr), p(self.col_idx),
-                                  p(self.part_ptr), p(self.part2node), self.n_local, d, P, *tune)
+        rc = lib.gnna_aggregate_f32_ex(int(mode), p(x_ext), self.n_ext, p(out), self.n_local,
+                                       p(self.row_ptr), p(self.col_idx),
+                                       p(self.degrees_ext) if mode == 1 else ctypes.c_void_p(0), float(eps),
+                                       p(self.part_ptr), p(self.part2node), d, P,
+                                       self.part_size, int(dim_worker), int(warp_per_block), st)
         _lib.check(rc, "sharded aggregate")
         return out
 

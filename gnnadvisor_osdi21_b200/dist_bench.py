@@ -1,0 +1,108 @@
+"""N > 1 arm of bench.py: the same aggregation step on a graph sharded over N GPUs of one node.
+
+One rank per GPU (torchrun), NCCL.  The graph is FIXED (the Reddit look-alike of the N=1 run), so this
+is strong scaling: rank r owns a contiguous vertex range holding ~E/N edges (dist.ShardedGraph), one
+step = halo exchange of the remote neighbour rows (gather + ONE all_to_all_single over NVLink) + the
+local aggregation kernel.  value = E_global * D / max-over-ranks device time.
+"""
+import json
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def run(args, bench):
+    from . import _lib, graph, dist as gdist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+
+    # every rank builds the same seeded graph on its own GPU, keeps its shard, drops the rest
+    gr = graph.lookalike(args.workload, device=device, scale=args.scale)
+    rp, ci = gr["row_ptr"], gr["col_idx"]
+    N, E, D = gr["num_nodes"], ci.numel(), args.dim
+    sg = gdist.ShardedGraph(rp, ci, args.part_size, device=device).build_tables()
+    gen = torch.Generator(device=device).manual_seed(20212)
+    X = torch.randn(N, D, device=device, generator=gen)
+    x_ext = sg.new_features(D)
+    sg.local(x_ext).copy_(X[sg.v0:sg.v0 + sg.n_local])
+    del X, rp, ci, gr["row_ptr"], gr["col_idx"]
+    torch.cuda.empty_cache()
+    out = torch.empty(sg.n_local, D, device=device)
+    P_local = sg.part2node.numel()
+
+    def step():
+        sg.aggregate(1, x_ext, out=out, dim_worker=args.dim_worker, warp_per_block=args.warp_per_block)
+
+    def kernel_only():
+        sg.aggregate(1, x_ext, out=out, dim_worker=args.dim_worker, warp_per_block=args.warp_per_block, do_exchange=False)
+
+    def exchange_only():
+        sg.exchange(x_ext)
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    barrier = lambda: dist.barrier(device_ids=[local])   # noqa: E731
+    sampler = bench.ClockSampler(local) if rank == 0 else None
+    step(); torch.cuda.synchronize()
+    _lib.launch_count(reset=True)
+    if sampler:
+        sampler.start()
+    ms = reduce_max(bench.timed(step, args.steps, args.warmup, barrier)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count() * args.steps // (args.steps + args.warmup)
+    k = max(3, args.steps // 4)
+    ms_kernel = reduce_max(bench.timed(kernel_only, k, 3, barrier)) / k
+    ms_exch = reduce_max(bench.timed(exchange_only, k, 3, barrier)) / k
+
+    # end to end: this rank's features start and end in pinned host memory
+    x_host = sg.local(x_ext).cpu().pin_memory()
+    out_host = torch.empty(sg.n_local, D).pin_memory()
+
+    def e2e_step():
+        sg.local(x_ext).copy_(x_host, non_blocking=True)
+        step()
+        out_host.copy_(out, non_blocking=True)
+    ke = max(3, min(args.steps, 30))
+    ms_e2e = reduce_max(bench.timed(e2e_step, ke, 3, barrier)) / ke
+
+    halo = sg.halo_bytes(D)
+    stats = torch.tensor([sg.num_edges_local, sg.n_local, sg.n_halo, P_local, halo["recv"], halo["send"]],
+                         device=device, dtype=torch.float64)
+    allstats = [torch.zeros_like(stats) for _ in range(world)]
+    dist.all_gather(allstats, stats)
+    if rank == 0:
+        peak, peak_src = bench.peak_gbs()
+        # roofline of the local kernel on the most loaded rank
+        per_rank = [[float(v) for v in s.cpu()] for s in allstats]
+        worst = max(per_rank, key=lambda s: s[0])
+        B = bench.alg_bytes(int(worst[0]), int(worst[1]), D, int(worst[3]))
+        achieved = B / (ms_kernel * 1e-3) / 1e9
+        line = {"metric": "aggregation throughput (GCN SpMM), edges*dim/s", "value": E * D / (ms * 1e-3), "unit": "edge*dim/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": bench.config_of(args, N, E, int(sum(s[3] for s in per_rank)),
+                                          {"parallelism": "1-D vertex-range shards x%d (edge-balanced), halo all_to_all per step" % world}),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "gnna::aggregate_kernel<float,4,16,1,false> on the most loaded shard",
+                             "alg_bytes_per_launch": B, "peak_source": peak_src,
+                             "note": "per-GPU kernel, exchange excluded; max over ranks of the kernel-only time"},
+                "e2e": {"value": E * D / (ms_e2e * 1e-3), "unit": "edge*dim/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(sum(s[1] for s in per_rank) * D * 4),
+                        "d2h_bytes_per_step": int(sum(s[1] for s in per_rank) * D * 4)},
+                "gpu_launches": int(launches), "clocks": clocks, "impl": "ours",
+                "extras": {"ms_kernel_only": ms_kernel, "ms_exchange_only": ms_exch,
+                           "shards": [{"edges": int(s[0]), "rows": int(s[1]), "halo_rows": int(s[2]),
+                                       "halo_recv_bytes": int(s[4]), "halo_send_bytes": int(s[5])} for s in per_rank]}}
+        print(json.dumps(line))
+    dist.barrier(device_ids=[local])
+    dist.destroy_process_group()

@@ -84,7 +84,7 @@ GNNA_API int gnna_sag_f32(const float *X, float *out,
                  int part_size, int dim_worker, int warp_per_block, void *stream);
 
 /* replaces spmm_forward_cuda_kernel / spmm_backward_cuda_kernel   kernel.cu:324-415, 478-552
- *   out[i,:] = sum_{j in N(i)} fl( fl(degrees[i]*degrees[j]) * X[j,:] )                     */
+ *   out[i,:] = sum_{j in N(i)} degrees[i]*degrees[j] * X[j,:]   (rounding: see gnna_set_gcn_exact)  */
 GNNA_API int gnna_gcn_aggregate_f32(const float *X, float *out,
                            const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
                            const int32_t *part_ptr, const int32_t *part2node,
@@ -98,6 +98,15 @@ GNNA_API int gnna_gin_aggregate_f32(const float *X, float *out,
                            const int32_t *part_ptr, const int32_t *part2node,
                            int64_t num_nodes, int dim, int64_t num_parts,
                            int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* Rectangular form used by the sharded (multi-GPU) path: X has num_src_rows rows (a rank's own rows
+ * followed by its halo rows), out has num_dst_rows <= num_src_rows rows; col_idx indexes X, part2node
+ * indexes out; degrees (GCN) has num_src_rows entries.  mode: 0 SAG, 1 GCN, 2 GIN.  No reference
+ * counterpart (the reference is single-GPU).                                                   */
+GNNA_API int gnna_aggregate_f32_ex(int mode, const float *X, int64_t num_src_rows, float *out, int64_t num_dst_rows,
+                                   const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
+                                   const int32_t *part_ptr, const int32_t *part2node, int dim, int64_t num_parts,
+                                   int part_size, int dim_worker, int warp_per_block, void *stream);
 
 /* bf16-storage variant: neighbour rows are gathered as bf16 (half the gather bytes), summed in
  * fp32 and written as fp32.  An extension: the reference is fp32-only.
@@ -145,6 +154,14 @@ GNNA_API int gnna_backward_gin_f32(const float *d_out, const float *x_agg, const
                           int64_t num_nodes, int din, int dout, int64_t num_parts,
                           int part_size, int dim_worker, int warp_per_block, void *stream);
 
+/* ---- vertex reordering ----------------------------------------------------------------------
+ * replaces the python module `rabbit` (rabbit_module/src/reorder.cpp:235-295, rabbit_order.hpp:393-673):
+ * Rabbit Order community-based renumbering.  Host code, deterministic.  The edge list may be directed
+ * and may contain duplicates and self loops (it is symmetrised internally, like the reference does).
+ * perm_old_to_new_host[v] = new id of vertex v (a permutation of 0..num_nodes-1).               */
+GNNA_API int gnna_rabbit_reorder_host(const int32_t *src_host, const int32_t *dst_host, int64_t num_edges,
+                                      int64_t num_nodes, int32_t *perm_old_to_new_host);
+
 /* ---- introspection (for tests, bench.py and the tuner) ------------------------------------
  * Launch geometry the library would use for a given call: fills lanes_per_row, chunks_per_lane,
  * vec_width, warps_per_block, grid_x, grid_y.  Returns GNNA_OK.                             */
@@ -160,6 +177,13 @@ typedef struct gnna_launch_info {
 } gnna_launch_info;
 GNNA_API int gnna_query_launch(int elem_bytes, int dim, int64_t num_parts, int dim_worker, int warp_per_block,
                       gnna_launch_info *info);
+
+/* GCN rounding: 0 (default) = out_i = n_i * sum_j (n_j * x_j): one pre-scale pass over the features,
+ * then a weight-free gather (no per-edge degrees[nid] gather; each term within 2 roundings of the
+ * reference's).  1 = the reference's per-edge fl(fl(n_i*n_j) * x_j) (kernel.cu:389,403), bit-identical
+ * to it for every node whose neighbours fit one group.  Also settable with GNNA_GCN_EXACT=1 in the
+ * environment.  Returns the previous setting.                                                  */
+GNNA_API int gnna_set_gcn_exact(int on);
 
 /* Number of kernels this library has launched on this thread since the last reset
  * (bench.py's "gpu_launches" is read from here, not guessed). */

@@ -53,5 +53,5 @@ def golden_terms(g, k, oracle):
     X, W, dO = np.abs(g[k + "X"]).astype(f64), np.abs(g[k + "W"]).astype(f64), np.abs(g[k + "dO"]).astype(f64)
     aG = oracle.closed_form(1, dO, rp, ci)                       # sum of |terms| of G = Ahat @ dO
     aS = np.abs(g[k + "forward_gin_agg"]).astype(f64)
-    return {"dX": aG @ W.T, "dW": X.T @ aG, "gin_out": oracle.closed_form(2, X, rp, ci, 0.5) @ W,
+    return {"fwd": oracle.closed_form(1, X @ W, rp, ci), "dX": aG @ W.T, "dW": X.T @ aG, "gin_out": oracle.closed_form(2, X, rp, ci, 0.5) @ W,
             "gin_dX": oracle.closed_form(2, dO @ W.T, rp, ci, 0.5), "gin_dW": aS.T @ dO}

@@ -126,10 +126,10 @@ def test_launch_geometry_follows_the_three_knobs():
     assert (q["lanes_per_row"], q["chunks_per_lane"], q["groups_per_warp"], q["warps_per_block"]) == (4, 4, 8, 2)
     q = ops.launch_info(16, 1000, 32, 4)
     assert (q["vec_width"], q["lanes_per_row"], q["groups_per_warp"]) == (4, 4, 8)
-    q = ops.launch_info(41, 10, 32, 4)
-    assert (q["vec_width"], q["lanes_per_row"], q["chunks_per_lane"], q["grid_y"]) == (1, 32, 2, 1)
-    q = ops.launch_info(3703, 10, 32, 2)
-    assert q["vec_width"] == 1 and q["grid_y"] == (3703 + 127) // 128
+    q = ops.launch_info(41, 10, 32, 4)          # fp32 rows are re-packed to 48 floats (whole sectors): 12 x 128-bit chunks
+    assert (q["vec_width"], q["lanes_per_row"], q["chunks_per_lane"], q["grid_y"]) == (4, 16, 1, 1)
+    q = ops.launch_info(3703, 10, 32, 2)        # citeseer GIN layer 1: 926 chunks, 128 per d-tile
+    assert q["vec_width"] == 4 and q["grid_y"] == (926 + 127) // 128
     q = ops.launch_info(64, 1000, 32, 8, elem_bytes=2)
     assert (q["vec_width"], q["lanes_per_row"]) == (8, 8)
 

@@ -38,6 +38,10 @@ class G:
     def gargs(self):
         return (self.d_rp, self.d_ci)
 
+    def terms(self, mode, X, eps=0.5):
+        """Sum of the absolute values of the terms each output element adds up (see helpers.assert_close)."""
+        return oracle.aggregate(mode, np.abs(X), self.ci, self.deg, eps, self.pp, self.pn)
+
     def pargs(self):
         return (self.d_pp, self.d_pn)
 
@@ -57,11 +61,11 @@ def test_aggregation_modes_all_dims(gname, dim):
     X = rand_features(g.n, dim, 100 + dim)
     dX = dev(X)
     out = ops.SAG(dX, *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 8)
-    assert_close(out.cpu().numpy(), oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="SAG")
+    assert_close(out.cpu().numpy(), oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="SAG", terms=g.terms(0, X))
     lib_gcn = _gcn_agg(dX, g, 32, 8)
-    assert_close(lib_gcn, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="GCN")
+    assert_close(lib_gcn, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="GCN", terms=g.terms(1, X))
     lib_gin = _gin_agg(dX, g, 0.5, 32, 8)
-    assert_close(lib_gin, oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn), what="GIN")
+    assert_close(lib_gin, oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn), what="GIN", terms=g.terms(2, X))
 
 
 def _gcn_agg(dX, g, dw, wpb):
@@ -94,7 +98,8 @@ def test_partsize_dimworker_sweep(ps, dw):
     rp, ci = GRAPHS["rmat"]()
     g = G(rp, ci, ps)
     X = rand_features(g.n, 64, 7)
-    assert_close(_gcn_agg(dev(X), g, dw, 4), oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="ps%d dw%d" % (ps, dw))
+    assert_close(_gcn_agg(dev(X), g, dw, 4), oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="ps%d dw%d" % (ps, dw),
+                 terms=g.terms(1, X))
 
 
 @pytest.mark.parametrize("wpb", [1, 2, 3, 8, 16, 32])
@@ -107,14 +112,38 @@ def test_warp_per_block_sweep(wpb):
 
 
 def test_single_group_nodes_are_bit_identical():
-    """A node whose neighbours fit one group is summed in the reference's order: exact equality."""
+    """A node whose neighbours fit one group is summed in the reference's order: exact equality for
+    SAG / GIN always, and for GCN in the reference-rounding mode (gnna_set_gcn_exact)."""
+    from gnnadvisor_osdi21_b200 import _lib
     rp, ci = make_graph("uniform", 2000, 12000, 31)
     assert (rp[1:] - rp[:-1]).max() <= 32
     g = G(rp, ci, 32)
-    X = rand_features(g.n, 64, 9)
-    for mode, ref in ((1, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn)), (2, oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn))):
-        got = _gcn_agg(dev(X), g, 32, 8) if mode == 1 else _gin_agg(dev(X), g, 0.5, 32, 8)
-        assert np.array_equal(got, ref), "mode %d" % mode
+    for dim in (64, 41):
+        X = rand_features(g.n, dim, 9)
+        assert np.array_equal(_gin_agg(dev(X), g, 0.5, 32, 8), oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn))
+        assert np.array_equal(ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 8).cpu().numpy(),
+                              oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn))
+        ref = oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn)
+        prev = _lib.set_gcn_exact(True)
+        try:
+            assert np.array_equal(_gcn_agg(dev(X), g, 32, 8), ref)
+        finally:
+            _lib.set_gcn_exact(prev)
+        assert_close(_gcn_agg(dev(X), g, 32, 8), ref, rtol=1e-5, what="prescaled GCN", terms=g.terms(1, X))   # a few ulp, not bitwise
+
+
+@pytest.mark.parametrize("dim", [7, 16, 64, 100])
+def test_gcn_exact_mode_all_paths(dim):
+    """The per-edge-rounding kernel (WEIGHTED template) stays covered: multi-group nodes, any dim."""
+    from gnnadvisor_osdi21_b200 import _lib
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 16)
+    X = rand_features(g.n, dim, 10)
+    prev = _lib.set_gcn_exact(True)
+    try:
+        assert_close(_gcn_agg(dev(X), g, 32, 8), oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="exact", terms=g.terms(1, X))
+    finally:
+        _lib.set_gcn_exact(prev)
 
 
 def test_layer_operators_against_oracle():
@@ -125,7 +154,8 @@ def test_layer_operators_against_oracle():
         X, W, dO = rand_features(n, din, 42), rand_weight(din, dout, 43), rand_features(n, dout, 44)
         dXd, dWd, dOd = dev(X), dev(W), dev(dO)
         out, = ops.forward(dXd, dWd, *g.gargs(), g.d_deg, *g.pargs(), ps, 32, 8)
-        assert_close(out.cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], what="forward")
+        assert_close(out.cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], what="forward",
+                     terms=g.terms(1, np.abs(X).astype(np.float64) @ np.abs(W)))
         dX, dW = ops.backward(dOd, dXd, dWd, *g.gargs(), g.d_deg, *g.pargs(), ps, 32, 8)
         odX, odW = oracle.backward(dO, X, W, rp, ci, g.deg, g.pp, g.pn)
         aG = np.abs(oracle.aggregate(1, dO, ci, g.deg, 1.0, g.pp, g.pn)).astype(np.float64)
@@ -157,7 +187,8 @@ def test_reference_cuda_golden(golden_dir):
         deg = ops.degrees_from_row_ptr(d_rp)
         X, W, dO = dev(gz[k + "X"]), dev(gz[k + "W"]), dev(gz[k + "dO"])
         assert_close(ops.SAG(X, d_rp, d_ci, deg, pp, pn, ps, dw, wpb).cpu().numpy(), gz[k + "SAG"], what=k + "SAG")
-        assert_close(ops.forward(X, W, d_rp, d_ci, deg, pp, pn, ps, dw, wpb)[0].cpu().numpy(), gz[k + "forward"], what=k + "forward")
+        assert_close(ops.forward(X, W, d_rp, d_ci, deg, pp, pn, ps, dw, wpb)[0].cpu().numpy(), gz[k + "forward"], what=k + "forward",
+                     terms=golden_terms(gz, k, oracle)["fwd"])
         dX, dW = ops.backward(dO, X, W, d_rp, d_ci, deg, pp, pn, ps, dw, wpb)
         t = golden_terms(gz, k, oracle)
         assert_close(dX.cpu().numpy(), gz[k + "backward_dX"], what=k + "dX", terms=t["dX"])
@@ -203,7 +234,7 @@ def test_isolated_nodes_and_f6_table():
         if not exact:
             assert g.pp[-1] == 0
         got = _gcn_agg(dev(X), g, 32, 4)
-        assert_close(got, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="exact=%s" % exact)
+        assert_close(got, oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="exact=%s" % exact, terms=g.terms(1, X))
         assert np.count_nonzero(got[deg == 0]) == 0
     # the F6 table drops the last group's neighbours, the exact one does not
     ge, gc = G(rp, ci, 32, exact=True), G(rp, ci, 32, exact=False)
@@ -280,7 +311,7 @@ def test_bf16_gather_path(dim):
     Xr = Xb.float().numpy()
     for mode in (0, 1, 2):
         got = ops.aggregate_bf16(mode, Xb.to(DEV), *g.gargs(), g.d_deg, 0.5, *g.pargs(), 32, 32, 8).cpu().numpy()
-        assert_close(got, oracle.aggregate(mode, Xr, ci, g.deg, 0.5, g.pp, g.pn), what="bf16 mode %d" % mode)
+        assert_close(got, oracle.aggregate(mode, Xr, ci, g.deg, 0.5, g.pp, g.pn), what="bf16 mode %d" % mode, terms=g.terms(mode, Xr))
 
 
 # ------------------------------------------------------------------------------------------ autograd layers
@@ -306,15 +337,20 @@ def test_gcn_and_gin_layers_autograd():
         x = dev(X).requires_grad_(True)
         y = conv(x, info)
         y.backward(dev(dO))
+        aX, aW, adO = np.abs(X).astype(np.float64), np.abs(W).astype(np.float64), np.abs(dO).astype(np.float64)
         if fwd is not None:
-            assert_close(y.detach().cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], what="gcn y")
+            assert_close(y.detach().cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], what="gcn y",
+                         terms=g.terms(1, aX @ aW))
             odX, odW = oracle.backward(dO, X, W, rp, ci, g.deg, g.pp, g.pn)
+            aG = g.terms(1, adO).astype(np.float64)
+            tX, tW = aG @ aW.T, aX.T @ aG
         else:
             oy, oS = oracle.forward_gin(X, W, rp, ci, 0.5, g.pp, g.pn)
-            assert_close(y.detach().cpu().numpy(), oy, what="gin y")
+            assert_close(y.detach().cpu().numpy(), oy, what="gin y", terms=g.terms(2, aX).astype(np.float64) @ aW)
             odX, odW = oracle.backward_gin(dO, oS, W, rp, ci, 0.5, g.pp, g.pn)
-        assert_close(x.grad.cpu().numpy(), odX, what="dX")
-        assert_close(conv.weights.grad.cpu().numpy(), odW, what="dW")
+            tX, tW = g.terms(2, adO @ aW.T), np.abs(oS.T).astype(np.float64) @ adO
+        assert_close(x.grad.cpu().numpy(), odX, what="dX", terms=tX)
+        assert_close(conv.weights.grad.cpu().numpy(), odW, what="dW", terms=tW)
 
 
 # ------------------------------------------------------------------------------------------ full-size properties
@@ -343,4 +379,6 @@ def test_full_size_properties(name, dim, scale):
     got = ops.forward(A, torch.eye(dim, device=DEV), rp, ci, deg, pp, pn, 32, 32, 8)[0].cpu().numpy()
     ref = oracle.aggregate(1, A.cpu().numpy(), ci.cpu().numpy(), deg.cpu().numpy(), 1.0,
                            pp.cpu().numpy(), pn.cpu().numpy(), threads=-1)
-    assert_close(got, ref, what=name)
+    terms = oracle.aggregate(1, A.abs().cpu().numpy(), ci.cpu().numpy(), deg.cpu().numpy(), 1.0,
+                             pp.cpu().numpy(), pn.cpu().numpy(), threads=-1)
+    assert_close(got, ref, what=name, terms=terms)

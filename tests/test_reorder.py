@@ -1,0 +1,81 @@
+"""Vertex reordering (rabbit replacement): a valid permutation, applied consistently, that improves
+locality on graphs with community structure.  CPU only (host code of the C-ABI library)."""
+import numpy as np
+import torch
+
+from gnnadvisor_osdi21_b200 import reorder as R
+
+
+def _span(e):
+    return float((e[0].long() - e[1].long()).abs().float().mean())
+
+
+def _clique_ring(nc, size, seed):
+    """nc cliques of `size` vertices joined in a ring, vertex ids randomly shuffled."""
+    rng = np.random.default_rng(seed)
+    src, dst = [], []
+    for c in range(nc):
+        base = c * size
+        for i in range(size):
+            for j in range(i + 1, size):
+                src.append(base + i); dst.append(base + j)
+        src.append(base); dst.append(((c + 1) % nc) * size)
+    src, dst = np.array(src), np.array(dst)
+    shuffle = rng.permutation(nc * size)
+    return torch.from_numpy(np.stack([shuffle[src], shuffle[dst]]).astype(np.int32))
+
+
+def test_permutation_is_valid_and_consistent():
+    e = _clique_ring(40, 12, 1)
+    n = 480
+    perm = R.permutation(e, n)
+    assert perm.dtype == torch.int32 and sorted(perm.tolist()) == list(range(n))
+    out = R.reorder(e)
+    assert out.shape == e.shape and out.dtype == torch.int32
+    assert torch.equal(out, perm[e.long()])                 # same edges, same order, relabelled endpoints
+    assert torch.equal(R.reorder(e), out)                   # deterministic
+
+
+def test_communities_become_contiguous():
+    e = _clique_ring(60, 10, 2)
+    out = R.reorder(e)
+    assert _span(out) < 0.1 * _span(e)
+    # every clique occupies one contiguous id range
+    perm = R.permutation(e, 600)
+    inv = torch.empty_like(perm); inv[perm.long()] = torch.arange(600, dtype=torch.int32)
+    und = torch.cat([e, e.flip(0)], 1)
+    adj = {}
+    for a, b in und.t().tolist():
+        adj.setdefault(a, set()).add(b)
+    for c_start in range(0, 600, 10):
+        members = inv[c_start:c_start + 10].tolist()
+        inside = sum(len(adj[m] & set(members)) for m in members)
+        assert inside >= 9 * 10 - 2          # a block of 10 new ids is (almost exactly) one clique
+
+
+def test_degenerate_inputs():
+    assert R.permutation(torch.zeros(2, 0, dtype=torch.int32), 5).tolist() == [0, 1, 2, 3, 4]
+    e = torch.tensor([[0, 1, 1, 2, 2], [0, 1, 2, 1, 2]], dtype=torch.int32)      # self loops + duplicates
+    perm = R.permutation(e, 4)
+    assert sorted(perm.tolist()) == [0, 1, 2, 3]
+    assert abs(int(perm[1]) - int(perm[2])) == 1
+
+
+def test_compat_modules_export_the_reference_names():
+    import importlib, os, sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnnadvisor_osdi21_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        for name, attrs in (("GNNAdvisor", ["SAG", "forward", "backward", "forward_gin", "backward_gin", "build_part"]),
+                            ("rabbit", ["reorder"]), ("dgl", ["DGLGraph"]), ("torch_sparse", ["spmm"])):
+            mod = importlib.import_module(name)
+            for a in attrs:
+                assert hasattr(mod, a), (name, a)
+        import torch_sparse
+        idx = torch.tensor([[0, 0, 1], [1, 1, 0]])
+        got = torch_sparse.spmm(idx, torch.ones(3), 2, 2, torch.tensor([[1., 2.], [3., 4.]]))
+        assert torch.equal(got, torch.tensor([[6., 8.], [1., 2.]]))
+    finally:
+        sys.path.remove(compat)
+        for name in ("GNNAdvisor", "rabbit", "dgl", "torch_sparse"):
+            sys.modules.pop(name, None)
