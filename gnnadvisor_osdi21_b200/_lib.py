@@ -48,6 +48,15 @@ SIGNATURES = {
                              + [i64, i32, i32, i64] + _TUNE),
     "gnna_backward_gin_f32": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, c_f32p] + _GRAPH + _PARTS
                               + [i64, i32, i32, i64] + _TUNE),
+    "gnna_ipc_alloc": (i32, [i64, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_ubyte * 64)]),
+    "gnna_ipc_open": (i32, [ctypes.POINTER(ctypes.c_ubyte * 64), ctypes.POINTER(ctypes.c_void_p)]),
+    "gnna_ipc_close": (i32, [ctypes.c_void_p]),
+    "gnna_ipc_free": (i32, [ctypes.c_void_p]),
+    "gnna_halo_push_f32": (i32, [c_f32p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_void_p),
+                                 ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
+                                 i32, i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
+    "gnna_halo_wait": (i32, [ctypes.c_void_p, i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
+    "gnna_halo_ack": (i32, [ctypes.POINTER(ctypes.c_void_p), i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
     "gnna_rabbit_reorder_host": (i32, [c_i32p, c_i32p, i64, i64, c_i32p]),
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
     "gnna_launch_count": (i64, [i32]),

@@ -142,11 +142,15 @@ class ShardedGraph:
     def halo_bytes(self, dim, elem=4):
         return {"recv": self.n_halo * dim * elem, "send": int(self.send_idx.numel()) * dim * elem}
 
-    def aggregate(self, mode, x_ext, out=None, eps=0.5, dim_worker=32, warp_per_block=8, do_exchange=True):
-        """out[n_local, D] = aggregation of this rank's rows (mode 0 SAG, 1 GCN, 2 GIN) over X_ext."""
+    def aggregate(self, mode, x_ext, out=None, eps=0.5, dim_worker=32, warp_per_block=8, do_exchange=True, peer=None):
+        """out[n_local, D] = aggregation of this rank's rows (mode 0 SAG, 1 GCN, 2 GIN) over X_ext.
+        peer: a PeerHalo -- x_ext is ignored, the step's buffer is peer.features(); the exchange is the
+        NVLink push kernel instead of gather + all_to_all."""
         from . import _lib
         assert self._tables_built, "call build_tables() first"
-        if do_exchange:
+        if peer is not None:
+            x_ext = peer.exchange() if do_exchange else peer.features(peer.step)
+        elif do_exchange:
             self.exchange(x_ext)
         d = x_ext.shape[1]
         if out is None:
@@ -161,7 +165,133 @@ class ShardedGraph:
                                        p(self.part_ptr), p(self.part2node), d, P,
                                        self.part_size, int(dim_worker), int(warp_per_block), st)
         _lib.check(rc, "sharded aggregate")
+        if peer is not None and do_exchange:
+            peer.ack()
         return out
+
+
+class _RawCuda:
+    """A raw device pointer dressed up for torch.as_tensor (no ownership)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerHalo:
+    """NVLink-native halo exchange (csrc/halo.cu): every rank maps its peers' feature buffers through
+    CUDA IPC, ONE kernel stores the rows a peer needs straight into that peer's halo rows and raises a
+    flag there; no gather buffer, no collective launch.  Feature buffers are double-buffered by step
+    parity; use `features(step)` to get the [n_ext, dim] tensor a step works on (fill its first n_local
+    rows), then `sg.aggregate(..., peer=True)`.
+
+    Collective constructor (all ranks of the group must call it)."""
+
+    def __init__(self, sg, dim):
+        from . import _lib
+        self.sg, self.dim, self.lib = sg, int(dim), _lib.load()
+        self.step = 0
+        dev, world, rank, group = sg.device, sg.world, sg.rank, sg.group
+        self._own = []
+        handles = torch.zeros(3, 64, dtype=torch.uint8)
+        ptrs = []
+        sizes = [max(sg.n_ext, 1) * self.dim * 4] * 2 + [64 * 4]
+        with torch.cuda.device(dev):
+            for i, nbytes in enumerate(sizes):
+                ptr = ctypes.c_void_p(0)
+                h = (ctypes.c_ubyte * 64)()
+                _lib.check(self.lib.gnna_ipc_alloc(nbytes, ctypes.byref(ptr), h), "ipc_alloc")
+                ptrs.append(ptr.value)
+                self._own.append(ptr.value)
+                handles[i] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
+        self.buf_ptr, self.ctrl_ptr = ptrs[:2], ptrs[2]
+        self.bufs = [torch.as_tensor(_RawCuda(p, (sg.n_ext, self.dim), "<f4"), device=dev) for p in self.buf_ptr]
+        # everyone learns everyone's handles, local row counts and per-source receive counts
+        gathered = [torch.zeros_like(handles) for _ in range(world)]
+        meta = torch.tensor([sg.n_local] + sg.recv_counts, dtype=torch.int64)
+        metas = [torch.zeros_like(meta) for _ in range(world)]
+        if dist.get_backend(group) == "nccl":
+            g_h = [t.to(dev) for t in gathered]
+            dist.all_gather(g_h, handles.to(dev), group=group)
+            gathered = [t.cpu() for t in g_h]
+            g_m = [t.to(dev) for t in metas]
+            dist.all_gather(g_m, meta.to(dev), group=group)
+            metas = [t.cpu() for t in g_m]
+        else:
+            dist.all_gather(gathered, handles, group=group)
+            dist.all_gather(metas, meta, group=group)
+        self.peer_buf = [[0] * world, [0] * world]
+        self.peer_ctrl = [0] * world
+        self._opened = []
+        with torch.cuda.device(dev):
+            for p in range(world):
+                if p == rank:
+                    self.peer_buf[0][p], self.peer_buf[1][p], self.peer_ctrl[p] = self.buf_ptr[0], self.buf_ptr[1], self.ctrl_ptr
+                    continue
+                opened = []
+                for i in range(3):
+                    h = (ctypes.c_ubyte * 64).from_buffer_copy(bytes(gathered[p][i].tolist()))
+                    ptr = ctypes.c_void_p(0)
+                    _lib.check(self.lib.gnna_ipc_open(h, ctypes.byref(ptr)), "ipc_open")
+                    opened.append(ptr.value)
+                    self._opened.append(ptr.value)
+                self.peer_buf[0][p], self.peer_buf[1][p], self.peer_ctrl[p] = opened
+        # where my block of rows starts inside peer p's buffer: after p's own rows and the blocks of lower ranks
+        self.dst_row0 = [0] * world
+        for p in range(world):
+            n_local_p = int(metas[p][0])
+            recv_p = [int(v) for v in metas[p][1:]]
+            self.dst_row0[p] = n_local_p + sum(recv_p[:rank])
+        sb = [0]
+        for c in sg.send_counts:
+            sb.append(sb[-1] + c)
+        self.send_begin = (ctypes.c_int32 * (world + 1))(*sb)
+        self.c_dst_row0 = (ctypes.c_int64 * world)(*self.dst_row0)
+        self.c_peer_ctrl = (ctypes.c_void_p * world)(*self.peer_ctrl)
+        self.c_peer_buf = [(ctypes.c_void_p * world)(*self.peer_buf[b]) for b in range(2)]
+        dist.barrier(group=group)
+
+    def features(self, step=None):
+        """The buffer step `step` (default: the next one) gathers from."""
+        s = self.step + 1 if step is None else step
+        return self.bufs[s & 1]
+
+    def exchange(self):
+        """Push my rows into my peers' halo rows for the next step and wait for theirs (on the current stream)."""
+        from . import _lib
+        sg = self.sg
+        self.step += 1
+        b = self.step & 1
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self.lib.gnna_halo_push_f32(ctypes.c_void_p(self.buf_ptr[b]),
+                                               ctypes.c_void_p(sg.send_idx.data_ptr() if sg.send_idx.numel() else 0),
+                                               self.send_begin, self.c_peer_buf[b], self.c_peer_ctrl, self.c_dst_row0,
+                                               ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.dim, self.step, st), "halo_push")
+        _lib.check(self.lib.gnna_halo_wait(ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.step, st), "halo_wait")
+        return self.bufs[b]
+
+    def ack(self):
+        """After the aggregation of the current step: producers may overwrite this parity again."""
+        from . import _lib
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self.lib.gnna_halo_ack(self.c_peer_ctrl, self.sg.world, self.sg.rank, self.step, st), "halo_ack")
+
+    def error(self):
+        """Non-zero if a bounded wait inside a kernel timed out (1: ack wait, 2: flag wait). Synchronises."""
+        torch.cuda.synchronize(self.sg.device)
+        ctrl = torch.as_tensor(_RawCuda(self.ctrl_ptr, (64,), "<i4"), device=self.sg.device)
+        return int(ctrl[48].item())
+
+    def close(self):
+        torch.cuda.synchronize(self.sg.device)
+        dist.barrier(group=self.sg.group)
+        self.bufs = []
+        with torch.cuda.device(self.sg.device):
+            for p in self._opened:
+                self.lib.gnna_ipc_close(ctypes.c_void_p(p))
+            dist.barrier(group=self.sg.group)
+            for p in self._own:
+                self.lib.gnna_ipc_free(ctypes.c_void_p(p))
+        self._opened, self._own = [], []
 
 
 def allreduce_weight_grad(d_weight, group=None):

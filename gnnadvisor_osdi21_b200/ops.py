@@ -173,16 +173,17 @@ def backward_gin(d_output, X, W, row_pointers, column_index, epsilon, part_point
 def aggregate_bf16(mode, X_bf16, row_pointers, column_index, degrees, epsilon, part_pointers, part2Node,
                    partSize, dimWorker, warpPerBlock):
     """Extension (no reference counterpart): gather bf16 rows, fp32 accumulate, fp32 out.
-    mode: 0 SAG, 1 GCN-normalised, 2 GIN."""
+    mode: 0 SAG, 1 GCN-normalised (per-edge weights), 2 GIN, 3 GCN on features already scaled by
+    degrees[j] (out_i = degrees[i] * sum_j X[j]; the fast path)."""
     _check_input(X_bf16, "X", torch.bfloat16)
     _graph_args(row_pointers, column_index, part_pointers, part2Node, X_bf16.device)
-    if mode == 1:
+    if mode in (1, 3):
         _check_input(degrees, "degrees", torch.float32)
     n, d = X_bf16.shape
     out = torch.empty((n, d), dtype=torch.float32, device=X_bf16.device)
     with torch.cuda.device(X_bf16.device):
         _lib.check(_lib.load().gnna_aggregate_bf16(int(mode), _ptr(X_bf16), _ptr(out), _ptr(row_pointers), _ptr(column_index),
-                                                   _ptr(degrees) if mode == 1 else ctypes.c_void_p(0), float(epsilon),
+                                                   _ptr(degrees) if mode in (1, 3) else ctypes.c_void_p(0), float(epsilon),
                                                    _ptr(part_pointers), _ptr(part2Node), n, d, part2Node.numel(),
                                                    int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
                    "aggregate_bf16")

@@ -110,7 +110,8 @@ GNNA_API int gnna_aggregate_f32_ex(int mode, const float *X, int64_t num_src_row
 
 /* bf16-storage variant: neighbour rows are gathered as bf16 (half the gather bytes), summed in
  * fp32 and written as fp32.  An extension: the reference is fp32-only.
- * mode: 0 = SAG, 1 = GCN (degrees), 2 = GIN (eps).                                           */
+ * mode: 0 = SAG, 1 = GCN (degrees, per-edge weights), 2 = GIN (eps), 3 = GCN on features the caller
+ * already scaled by degrees[j] (out_i = degrees[i] * sum_j X[j]: no per-edge degree gather).     */
 GNNA_API int gnna_aggregate_bf16(int mode, const void *X_bf16, float *out_f32,
                         const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
                         const int32_t *part_ptr, const int32_t *part2node,
@@ -153,6 +154,29 @@ GNNA_API int gnna_backward_gin_f32(const float *d_out, const float *x_agg, const
                           const int32_t *part_ptr, const int32_t *part2node,
                           int64_t num_nodes, int din, int dout, int64_t num_parts,
                           int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* ---- NVLink-native halo exchange for the sharded path (csrc/halo.cu; no reference counterpart) ------
+ * Device memory that other processes on the node can map (CUDA IPC): alloc returns a zeroed buffer and
+ * its 64-byte handle; peers open / close it; the owner frees it.                                   */
+GNNA_API int gnna_ipc_alloc(int64_t bytes, void **ptr, unsigned char *handle64);
+GNNA_API int gnna_ipc_open(const unsigned char *handle64, void **ptr);
+GNNA_API int gnna_ipc_close(void *ptr);
+GNNA_API int gnna_ipc_free(void *ptr);
+
+/* One exchange step.  push: ONE kernel copies, for every peer p, rows x_local[send_idx[send_begin[p] ..
+ * send_begin[p+1])] into rows peer_dst_row0[p].. of peer p's mapped feature buffer (128-bit stores over
+ * NVLink) and then stores `step` into flags[my_rank] of p's control block (release, system scope).
+ * wait: returns (on the stream) once every peer's flag in MY control block reached `step`.
+ * ack: after the aggregation that read the halo rows, stores `step` into acks[my_rank] of every peer so
+ * the buffer of this step parity may be overwritten at step+2 (push waits for it).  Control block:
+ * 64 uint32 in IPC memory: [0,16) flags, [16,32) acks, [32,48) scratch, [48] error word (non-zero:
+ * a bounded wait timed out).  step counts 1, 2, 3, ...; *_host arrays have `world` entries.          */
+GNNA_API int gnna_halo_push_f32(const float *x_local, const int64_t *send_idx, const int32_t *send_begin_host,
+                                void *const *peer_feature_base_host, void *const *peer_ctrl_host,
+                                const int64_t *peer_dst_row0_host, void *my_ctrl,
+                                int world, int my_rank, int dim, uint32_t step, void *stream);
+GNNA_API int gnna_halo_wait(void *my_ctrl, int world, int my_rank, uint32_t step, void *stream);
+GNNA_API int gnna_halo_ack(void *const *peer_ctrl_host, int world, int my_rank, uint32_t step, void *stream);
 
 /* ---- vertex reordering ----------------------------------------------------------------------
  * replaces the python module `rabbit` (rabbit_module/src/reorder.cpp:235-295, rabbit_order.hpp:393-673):

@@ -312,6 +312,11 @@ def test_bf16_gather_path(dim):
     for mode in (0, 1, 2):
         got = ops.aggregate_bf16(mode, Xb.to(DEV), *g.gargs(), g.d_deg, 0.5, *g.pargs(), 32, 32, 8).cpu().numpy()
         assert_close(got, oracle.aggregate(mode, Xr, ci, g.deg, 0.5, g.pp, g.pn), what="bf16 mode %d" % mode, terms=g.terms(mode, Xr))
+    # mode 3: the caller pre-scales by n_j (and rounds THAT to bf16); out_i = n_i * sum_j Xs_j
+    Xs = (torch.from_numpy(Xr) * torch.from_numpy(g.deg)[:, None]).to(torch.bfloat16)
+    got = ops.aggregate_bf16(3, Xs.to(DEV), *g.gargs(), g.d_deg, 0.5, *g.pargs(), 32, 32, 8).cpu().numpy()
+    ref = g.deg[:, None].astype(np.float64) * oracle.closed_form(0, Xs.float().numpy(), rp, ci)
+    assert_close(got, ref, what="bf16 prescaled", terms=g.deg[:, None] * oracle.closed_form(0, np.abs(Xs.float().numpy()), rp, ci))
 
 
 # ------------------------------------------------------------------------------------------ autograd layers
