@@ -48,6 +48,8 @@ SIGNATURES = {
                              + [i64, i32, i32, i64] + _TUNE),
     "gnna_backward_gin_f32": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, c_f32p] + _GRAPH + _PARTS
                               + [i64, i32, i32, i64] + _TUNE),
+    "gnna_aggregate_gemm_fused_bf16": (i32, [i32, ctypes.c_void_p, i32, c_f32p, ctypes.c_float, c_f32p, c_f32p] + _GRAPH
+                                       + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
     "gnna_ipc_alloc": (i32, [i64, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_ubyte * 64)]),
     "gnna_ipc_open": (i32, [ctypes.POINTER(ctypes.c_ubyte * 64), ctypes.POINTER(ctypes.c_void_p)]),
     "gnna_ipc_close": (i32, [ctypes.c_void_p]),

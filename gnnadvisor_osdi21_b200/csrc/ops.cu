@@ -197,8 +197,9 @@ extern "C" int gnna_backward_gin_f32(const float *d_out, const float *x_agg, con
                                      int part_size, int dim_worker, int warp_per_block, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    GNNA_REQUIRE(d_out && x_agg && W && Pm_ws && d_input && d_weight, "gnna_backward_gin_f32: null pointer");
+    GNNA_REQUIRE(d_out && x_agg && W && d_weight && (!d_input || Pm_ws), "gnna_backward_gin_f32: null pointer");
     GNNA_TRY(sgemm_rm(st, true, false, din, dout, num_nodes, x_agg, d_out, d_weight));    // kernel.cu:710
+    if (!d_input) return GNNA_OK;                                                          // caller needs no input gradient
     GNNA_TRY(sgemm_rm(st, false, true, num_nodes, din, dout, d_out, W, Pm_ws));           // :711
     return aggregate(MODE_GIN, 4, Pm_ws, d_input, row_ptr, col_idx, nullptr, eps, part_ptr, part2node, num_nodes, din,
                      num_parts, part_size, dim_worker, warp_per_block, st);               // :712-738

@@ -52,8 +52,11 @@ class GNNAFunction(torch.autograd.Function):
     def backward(ctx, d_output):
         X, weight = ctx.saved_tensors
         info = ctx.inputInfo
+        # unlike the reference (kernel.cu:472 runs G @ W^T unconditionally) the input gradient is only
+        # computed when autograd asks for it: the first layer's features need none
         d_input, d_weight = GNNA.backward(d_output.contiguous(), X, weight, *_graph(info), info.degrees,
-                                          info.partPtr, info.part2Node, *ctx.tune)
+                                          info.partPtr, info.part2Node, *ctx.tune,
+                                          need_d_input=ctx.needs_input_grad[0])
         return d_input, d_weight, None
 
 
@@ -75,7 +78,8 @@ class GNNAFunction_GIN(torch.autograd.Function):
         X_agg, weight = ctx.saved_tensors
         info = ctx.inputInfo
         d_input, d_weight = GNNA.backward_gin(d_output.contiguous(), X_agg, weight, *_graph(info), ctx.eplison,
-                                              info.partPtr, info.part2Node, *ctx.tune)
+                                              info.partPtr, info.part2Node, *ctx.tune,
+                                              need_d_input=ctx.needs_input_grad[0])
         return d_input, d_weight, None, None
 
 

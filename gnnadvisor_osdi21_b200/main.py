@@ -1,0 +1,167 @@
+"""Training / verification / single-kernel driver with the command line of the reference's GNNA_main.py.
+
+    python -m gnnadvisor_osdi21_b200.main --dataDir ../osdi-ae-graphs --dataset amazon0505 --dim 96 \\
+        --hidden 16 --classes 22 --model gcn --partSize 32 --dimWorker 32 --warpPerBlock 4
+
+Same 17 flags, same string booleans and the same output lines (`Time (ms): ...`, `# Verification
+PASSED`, `=> SpMM profiling avg (ms): ...`) as GNNAdvisor/GNNA_main.py:15-50,116-137,189-202, so the
+reference's batch drivers and log scrapers (0_bench_*.py, 1_log2csv.py) work on it.  Additions:
+`--synthetic NAME[:scale]` builds a look-alike graph when no dataset file exists (there are none
+offline), `--decider b200` uses the re-tuned parameter choice in auto mode.
+The reference's own GNNA_main.py also runs unchanged on this runtime: put
+gnnadvisor_osdi21_b200/compat on PYTHONPATH (option A).
+"""
+import argparse
+import os.path as osp
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import graph, layers, ops
+from .param import InputProperty
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--dataDir", type=str, default="../osdi-ae-graphs", help="the path to graphs")
+    p.add_argument("--dataset", type=str, default="amazon0601", help="dataset")
+    p.add_argument("--dim", type=int, default=96, help="input embedding dimension size")
+    p.add_argument("--hidden", type=int, default=16, help="hidden dimension size")
+    p.add_argument("--classes", type=int, default=22, help="output classes size")
+    p.add_argument("--model", type=str, default="gcn", choices=["gcn", "gin"], help="GCN or GIN")
+    p.add_argument("--num_epoches", type=int, default=200, help="number of epoches for training, default=200")
+    p.add_argument("--partSize", type=int, default=32, help="neighbor-group size")
+    p.add_argument("--dimWorker", type=int, default=32, help="number of worker threads (MUST < 32)")
+    p.add_argument("--warpPerBlock", type=int, default=4, help="number of warp per block, recommended: GCN: 8, GIN: 2")
+    p.add_argument("--sharedMem", type=int, default=100, help="shared memory size of each block (KB)")
+    for flag, default, text in (("manual_mode", "True", "True: use manual config, False: auto config"),
+                                ("verbose_mode", "False", "True: verbose mode"),
+                                ("enable_rabbit", "False", "True: enable rabbit reordering"),
+                                ("loadFromTxt", "False", "True: load the graph TXT edge list, False: load from .npz"),
+                                ("single_spmm", "False", "True: profile the single SpMM kernel for num_epoches times"),
+                                ("verify_spmm", "False", "True: verify a single SpMM against the CPU reference")):
+        p.add_argument("--" + flag, type=str, choices=["True", "False"], default=default, help=text)
+    p.add_argument("--synthetic", type=str, default="", help="look-alike graph name[:scale] instead of a dataset file")
+    p.add_argument("--decider", type=str, default="reference", choices=["reference", "b200"], help="auto-mode parameter choice")
+    return p
+
+
+def load_dataset(args, device, verbose):
+    if args.synthetic:
+        name, _, scale = args.synthetic.partition(":")
+        gr = graph.lookalike(name, device=device, scale=float(scale) if scale else 1.0)
+        return graph.GraphDataset(args.dim, args.classes, csr=(gr["row_ptr"], gr["col_idx"]), device=device, verbose=verbose)
+    if args.loadFromTxt == "True":
+        path = osp.join(args.dataDir, args.dataset)
+    else:
+        path = osp.join(args.dataDir, args.dataset + ".npz")
+    return graph.GraphDataset(args.dim, args.classes, path=path, device=device, verbose=verbose)
+
+
+def verify_spmm(info, dataset, hidden):
+    """unitest.py:33-63: SAG on all-ones features against a CPU sparse product of the RAW edge list; pass when
+    all but 1e-4 of the elements are exactly equal."""
+    n = dataset.num_nodes
+    X = torch.ones(n, hidden)
+    print("# Compute result on GPU")
+    got = ops.SAG(X.to(info.row_pointers.device), info.row_pointers, info.column_index, info.degrees,
+                  info.partPtr, info.part2Node, info.partSize, info.dimWorker, info.warpPerBlock).cpu()
+    print("# Compute reference on CPU")
+    idx = torch.as_tensor(dataset.edge_index, dtype=torch.int64)
+    ref = torch.sparse.mm(torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)), X)
+    ok = (1 - torch.eq(ref, got).sum().item() / ref.numel()) < 1e-4
+    print("# Verification PASSED" if ok else "# Verification FAILED")
+    return ok
+
+
+def profile_spmm(info, hidden, rounds):
+    """unitest.py:65-80: 10 dry runs + `rounds` timed SAG calls between two synchronisations."""
+    n = info.row_pointers.numel() - 1
+    X = torch.ones(n, hidden, device=info.row_pointers.device)
+    print("SpMM profiling size: N: {}, N: {}, K: {}".format(n, n, hidden))
+    call = lambda: ops.SAG(X, info.row_pointers, info.column_index, info.degrees, info.partPtr, info.part2Node,   # noqa: E731
+                           info.partSize, info.dimWorker, info.warpPerBlock)
+    for _ in range(10):
+        call()
+    torch.cuda.synchronize()
+    start = time.perf_counter()
+    for _ in range(rounds):
+        call()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - start) * 1e3 / rounds
+    print("=> SpMM profiling avg (ms): {:.3f}".format(ms))
+    print()
+    return ms
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    print(args)
+    verbose = args.verbose_mode == "True"
+    assert torch.cuda.is_available()                      # GNNA_main.py:53
+    device = torch.device("cuda")
+    dataset = load_dataset(args, device, verbose)
+    info = InputProperty(dataset.row_pointers, dataset.column_index, dataset.degrees,
+                         args.partSize, args.dimWorker, args.warpPerBlock, args.sharedMem,
+                         hiddenDim=args.hidden, dataset_obj=dataset, enable_rabbit=args.enable_rabbit == "True",
+                         manual_mode=args.manual_mode == "True", verbose=verbose)
+    if args.manual_mode != "True" and args.decider == "b200":
+        info.decider_b200()
+    else:
+        info.decider()
+    info.set_input()
+    info.print_param()
+    info.set_hidden()
+    info.print_param()
+
+    start = time.perf_counter()
+    part_ptr, part2node = ops.build_part(info.partSize, info.row_pointers)       # GNNA_main.py:102
+    if verbose:
+        print("# Build nb_part (s): {:.3f}".format(time.perf_counter() - start))
+    info.row_pointers = info.row_pointers.to(device)
+    info.column_index = info.column_index.to(device)
+    info.partPtr = part_ptr.int().to(device)                                     # :109-110
+    info.part2Node = part2node.int().to(device)
+    info.degrees = dataset.degrees.to(device)     # refreshed after a reorder (the reference keeps the stale ones, F11)
+
+    if args.verify_spmm == "True":
+        return 0 if verify_spmm(info, dataset, args.hidden) else 1
+    if args.single_spmm == "True":
+        profile_spmm(info, args.hidden, args.num_epoches)
+        return 0
+
+    conv = layers.GCNConv if args.model == "gcn" else layers.GINConv
+    dims = ([dataset.num_features, args.hidden, dataset.num_classes] if args.model == "gcn"
+            else [dataset.num_features] + [args.hidden] * 4 + [dataset.num_classes])     # GNNA_main.py:142-171
+    convs = torch.nn.ModuleList([conv(a, b) for a, b in zip(dims[:-1], dims[1:])]).to(device)
+    if verbose:
+        print(convs)
+    optimizer = torch.optim.Adam(convs.parameters(), lr=0.01)
+    x, y = dataset.x, dataset.y
+
+    def train():
+        optimizer.zero_grad()
+        h = x
+        for i, c in enumerate(convs):
+            h = c(h, info.set_input() if i == 0 else info.set_hidden())
+            if i < len(convs) - 1:
+                h = F.relu(h)
+        F.nll_loss(F.log_softmax(h, dim=1), y).backward()
+        optimizer.step()
+
+    for _ in range(10):                                                           # dry run, :191-192
+        train()
+    torch.cuda.synchronize()
+    start = time.perf_counter()
+    for _ in range(args.num_epoches):
+        train()
+    torch.cuda.synchronize()
+    print("Time (ms): {:.3f}".format((time.perf_counter() - start) * 1e3 / args.num_epoches))
+    print()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -25,7 +25,8 @@ import torch
 from . import _lib
 
 __all__ = ["SAG", "forward", "backward", "forward_gin", "backward_gin", "build_part",
-           "build_part_exact", "aggregate_bf16", "degrees_from_row_ptr", "launch_info"]
+           "build_part_exact", "aggregate_bf16", "aggregate_gemm_fused", "forward_gin_fused",
+           "degrees_from_row_ptr", "launch_info"]
 
 
 def _check_input(t, name, dtype=None):
@@ -100,9 +101,12 @@ def forward(input, weight, row_pointers, column_index, degrees, part_pointers, p
 
 
 def backward(d_output, X, W, row_pointers, column_index, degrees, part_pointers, part2Node,
-             partSize, dimWorker, warpPerBlock):
+             partSize, dimWorker, warpPerBlock, need_d_input=True):
     """GCN backward: G = Ahat @ d_output; returns [G @ W^T, X^T @ G].
-    Reference: spmm_backward, GNNAdvisor.cpp:124-150; kernel.cu:422-552."""
+    Reference: spmm_backward, GNNAdvisor.cpp:124-150; kernel.cu:422-552.
+    need_d_input=False (keyword only in spirit; the reference has no such argument) skips the G @ W^T
+    product and returns None for it -- the reference computes it even for the first layer, whose input
+    needs no gradient (a 561 MB write on Reddit)."""
     _feat2d(d_output, "d_output")
     _feat2d(X, "X")
     _feat2d(W, "W")
@@ -113,7 +117,7 @@ def backward(d_output, X, W, row_pointers, column_index, degrees, part_pointers,
     if X.shape[0] != n or W.shape[0] != din or W.shape[1] != dout:
         raise RuntimeError("size mismatch: d_output %s, X %s, W %s" % (tuple(d_output.shape), tuple(X.shape), tuple(W.shape)))
     g = torch.empty_like(d_output)
-    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device)
+    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device) if need_d_input else None
     d_weight = torch.empty((din, dout), dtype=torch.float32, device=X.device)
     with torch.cuda.device(X.device):
         _lib.check(_lib.load().gnna_backward_f32(_ptr(d_output), _ptr(X), _ptr(W), _ptr(g), _ptr(d_input), _ptr(d_weight),
@@ -146,7 +150,7 @@ def forward_gin(input, weight, row_pointers, column_index, epsilon, part_pointer
 
 
 def backward_gin(d_output, X, W, row_pointers, column_index, epsilon, part_pointers, part2Node,
-                 partSize, dimWorker, warpPerBlock):
+                 partSize, dimWorker, warpPerBlock, need_d_input=True):
     """GIN backward (X is the saved X_agg): d_W = X^T @ d_output; d_X = eps * A @ (d_output @ W^T).
     Reference: spmm_backward_gin, GNNAdvisor.cpp:183-207; kernel.cu:696-814."""
     _feat2d(d_output, "d_output")
@@ -157,8 +161,8 @@ def backward_gin(d_output, X, W, row_pointers, column_index, epsilon, part_point
     din = X.shape[1]
     if X.shape[0] != n or W.shape[0] != din or W.shape[1] != dout:
         raise RuntimeError("size mismatch: d_output %s, X %s, W %s" % (tuple(d_output.shape), tuple(X.shape), tuple(W.shape)))
-    pm = torch.empty((n, din), dtype=torch.float32, device=X.device)
-    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device)
+    pm = torch.empty((n, din), dtype=torch.float32, device=X.device) if need_d_input else None
+    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device) if need_d_input else None
     d_weight = torch.empty((din, dout), dtype=torch.float32, device=X.device)
     with torch.cuda.device(X.device):
         _lib.check(_lib.load().gnna_backward_gin_f32(_ptr(d_output), _ptr(X), _ptr(W), float(epsilon), _ptr(pm),
@@ -188,6 +192,41 @@ def aggregate_bf16(mode, X_bf16, row_pointers, column_index, degrees, epsilon, p
                                                    int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
                    "aggregate_bf16")
     return out
+
+
+def aggregate_gemm_fused(mode, X, weight, row_pointers, column_index, degrees, epsilon, part_pointers, part2Node,
+                         partSize, dimWorker, warpPerBlock, want_agg=True):
+    """Extension: (c_i * sum_j X_j) @ W in ONE kernel -- gather into shared memory, bf16 tcgen05.mma with the
+    accumulator in TMEM (csrc/fused_gemm.cu).  mode 0 SAG, 2 GIN (c = eps), 3 GCN on pre-scaled X
+    (c_i = degrees[i]).  X fp32 or bf16; returns [out fp32, X_agg fp32 or None]."""
+    if X.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("X must be float32 or bfloat16")
+    _check_input(X, "X")
+    _feat2d(weight, "weight")
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, X.device)
+    if mode == 3:
+        _check_input(degrees, "degrees", torch.float32)
+    n, din = X.shape
+    if weight.shape[0] != din:
+        raise RuntimeError("size mismatch: X [%d, %d] x weight [%d, %d]" % (n, din, weight.shape[0], weight.shape[1]))
+    dout = weight.shape[1]
+    out = torch.empty((n, dout), dtype=torch.float32, device=X.device)
+    x_agg = torch.empty((n, din), dtype=torch.float32, device=X.device) if want_agg else None
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().gnna_aggregate_gemm_fused_bf16(
+            int(mode), _ptr(X), 1 if X.dtype == torch.bfloat16 else 0, _ptr(weight), float(epsilon), _ptr(out), _ptr(x_agg),
+            _ptr(row_pointers), _ptr(column_index), _ptr(degrees) if mode == 3 else ctypes.c_void_p(0),
+            _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+            int(partSize), int(dimWorker), int(warpPerBlock), _stream()), "aggregate_gemm_fused")
+    return [out, x_agg]
+
+
+def forward_gin_fused(input, weight, row_pointers, column_index, epsilon, part_pointers, part2Node,
+                      partSize, dimWorker, warpPerBlock):
+    """forward_gin with the X_agg @ W product on the tensor cores (bf16 operands, fp32 accumulate), fused
+    behind the aggregation.  Same return as forward_gin: [out, X_agg]; X_agg is exact fp32."""
+    return aggregate_gemm_fused(2, input, weight, row_pointers, column_index, None, epsilon, part_pointers, part2Node,
+                                partSize, dimWorker, warpPerBlock)
 
 
 # ------------------------------------------------------------------------------------------ build_part

@@ -82,6 +82,40 @@ class InputProperty(object):
         self._say("\n=> AUTO Decider Complete !!!\n")
         return self
 
+    # ------------------------------------------------------------------ Decider re-tuned for B200
+    @staticmethod
+    def b200_choice(avg_degree, dim):
+        """(partSize, dimWorker, warpPerBlock) for csrc/aggregate.cu on B200, from the parameter studies in
+        profiles/r01_params_*.txt (the reference's s7-4_1 / s7-4_2 sweeps re-run on the new kernel):
+          * partSize: 16..64 is flat and best; partSize = avgDegree (the reference's rule, param.py:73) costs
+            9 % on Reddit (491) and 3x on sparse graphs (2..4).  32 for avgDegree >= 24, else 16.
+          * dimWorker: lanes per neighbour row.  Half the row's 16-byte chunks (two chunks per lane, twice as
+            many groups in flight per warp) is 7 % faster than one chunk per lane when HBM-bound and equal
+            when L2-bound; never fewer than 4 lanes.
+          * warpPerBlock: 2..4 is best (smaller CTAs retire and refill faster); 4."""
+        part_size = 32 if avg_degree >= 24 else 16
+        chunks = (int(dim) + 3) // 4
+        need = 1
+        while need < chunks and need < 32:
+            need *= 2
+        dim_worker = max(4, need // 2) if need >= 16 else max(min(need, 4), need)
+        return part_size, dim_worker, 4
+
+    def decider_b200(self):
+        """Auto mode with the B200 choices instead of the reference's sm_86 heuristics; same fields are set."""
+        self.partSize, self.dimWorker_input, self.warpPerBlock_input = self.b200_choice(self.avgNodeDegree, self.inputDim)
+        _, self.dimWorker_hidden, self.warpPerBlock_hidden = self.b200_choice(self.avgNodeDegree, self.hiddenDim)
+        self.dimWorker, self.warpPerBlock = self.dimWorker_hidden, self.warpPerBlock_hidden
+        if self.enable_rabbit:
+            want = math.sqrt(self.avgEdgeSpan) > math.sqrt(self.num_nodes) / 100      # the reference's test (:110)
+            self.dataset_obj.reorder_flag = want
+            self.reorder_status = want
+            self.dataset_obj.rabbit_reorder()
+            if want:   # unlike the reference (SURVEY.md F11) the reordered CSR is picked up in auto mode too
+                self.row_pointers, self.column_index = self.dataset_obj.row_pointers, self.dataset_obj.column_index
+        self._say("\n=> B200 Decider Complete !!!\n")
+        return self
+
     # ------------------------------------------------------------------ per-layer switch (param.py:122-141)
     def set_input(self):
         self.dimWorker, self.warpPerBlock = self.dimWorker_input, self.warpPerBlock_input

@@ -147,13 +147,29 @@ GNNA_API int gnna_forward_gin_f32(const float *X, const float *W, float eps, flo
                          int part_size, int dim_worker, int warp_per_block, void *stream);
 
 /* replaces spmm_backward_cuda_gin     kernel.cu:696-747   dW = S^T*dOut ; Pm = dOut*W^T ; dX = eps*A*Pm
- *   Pm_ws [N,din] scratch, d_input [N,din], d_weight [din,dout]                             */
+ *   Pm_ws [N,din] scratch, d_input [N,din] (may be NULL: only dW is computed), d_weight [din,dout] */
 GNNA_API int gnna_backward_gin_f32(const float *d_out, const float *x_agg, const float *W, float eps,
                           float *Pm_ws, float *d_input, float *d_weight,
                           const int32_t *row_ptr, const int32_t *col_idx,
                           const int32_t *part_ptr, const int32_t *part2node,
                           int64_t num_nodes, int din, int dout, int64_t num_parts,
                           int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* ---- fused aggregate -> X*W on the tensor cores (csrc/fused_gemm.cu) -----------------------------------
+ * out = (c_i * sum_{j in N(i)} X[j,:]) * W in ONE kernel: a CTA gathers 128 destination rows into shared
+ * memory, converts them to bf16 and multiplies by W (bf16) with tcgen05.mma, fp32 accumulation in TMEM.
+ * Fuses what the reference does as aggregation kernel + torch::mm (spmm_forward_cuda_gin, kernel.cu:559-617)
+ * for the bf16 configuration of BASELINE.json; the fp32 operators above stay bit-faithful and unfused.
+ *   mode 0: c_i = 1 (SAG)   2: c_i = eps (GIN forward)   3: c_i = degrees[i], X already scaled by degrees[j] (GCN)
+ *   X [N, din] fp32 (x_is_bf16 = 0) or bf16 (1); W [din, dout] fp32 (rounded to bf16 inside); out [N, dout] fp32;
+ *   x_agg [N, din] fp32 receives the aggregated features (may be NULL).  Supported: din in {32, 64, 128} (fp32 X)
+ *   or {64, 128, 256} (bf16 X), 1 <= dout <= 256; GNNA_ERR_UNSUPPORTED otherwise.                      */
+GNNA_API int gnna_aggregate_gemm_fused_bf16(int mode, const void *X, int x_is_bf16, const float *W, float eps,
+                                            float *out, float *x_agg,
+                                            const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                                            const int32_t *part_ptr, const int32_t *part2node,
+                                            int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                            int part_size, int dim_worker, int warp_per_block, void *stream);
 
 /* ---- NVLink-native halo exchange for the sharded path (csrc/halo.cu; no reference counterpart) ------
  * Device memory that other processes on the node can map (CUDA IPC): alloc returns a zeroed buffer and

@@ -199,3 +199,17 @@ def test_param_layer_switch_and_manual_mode():
     assert p.set_hidden().warpPerBlock == 7 and not p.state_set_input
     with pytest.raises(ValueError):
         param.inputProperty(dataset_obj=None)
+
+
+def test_b200_decider_choices():
+    """re-tuned (partSize, dimWorker, warpPerBlock) from the B200 parameter studies."""
+    c = param.InputProperty.b200_choice
+    assert c(492.0, 64) == (32, 8, 4)       # Reddit hidden layer
+    assert c(50.5, 128) == (32, 16, 4)
+    assert c(11.9, 16) == (16, 4, 4)        # amazon0505 hidden 16
+    assert c(3.9, 1433) == (16, 16, 4)      # Cora input layer
+    ds = _FakeDataset(232965, 114615892, 602, 70000.0)
+    p = param.InputProperty(None, None, None, 32, 32, 4, 100, hiddenDim=64, dataset_obj=ds, enable_rabbit=True, manual_mode=False)
+    p.decider_b200()
+    assert (p.partSize, p.dimWorker_input, p.dimWorker_hidden, p.warpPerBlock_input) == (32, 16, 8, 4)
+    assert ds.reordered == 1 and p.reorder_status
