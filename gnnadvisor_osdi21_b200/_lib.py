@@ -40,6 +40,9 @@ SIGNATURES = {
     "gnna_gin_aggregate_f32": (i32, [c_f32p, c_f32p] + _GRAPH + [ctypes.c_float] + _PARTS + [i64, i32, i64] + _TUNE),
     "gnna_aggregate_f32_ex": (i32, [i32, c_f32p, i64, c_f32p, i64] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
                               + [i32, i64] + _TUNE),
+    "gnna_aggregate_part_f32_ex": (i32, [i32, i32, c_f32p, i64, c_f32p, i64] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
+                                   + [i32, i64] + _TUNE),
+    "gnna_prescale_rows_f32": (i32, [c_f32p, c_f32p, c_f32p, i64, i32, ctypes.c_void_p]),
     "gnna_aggregate_bf16": (i32, [i32, ctypes.c_void_p, c_f32p] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
                             + [i64, i32, i64] + _TUNE),
     "gnna_forward_f32": (i32, [c_f32p] * 4 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
@@ -56,9 +59,10 @@ SIGNATURES = {
     "gnna_ipc_free": (i32, [ctypes.c_void_p]),
     "gnna_halo_push_f32": (i32, [c_f32p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_void_p),
                                  ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
-                                 i32, i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
+                                 i32, i32, i32, ctypes.c_void_p]),
+    "gnna_halo_begin_step": (i32, [ctypes.c_void_p, ctypes.c_void_p]),
     "gnna_halo_wait": (i32, [ctypes.c_void_p, i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
-    "gnna_halo_ack": (i32, [ctypes.POINTER(ctypes.c_void_p), i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
+    "gnna_halo_ack": (i32, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, i32, i32, ctypes.c_void_p]),
     "gnna_rabbit_reorder_host": (i32, [c_i32p, c_i32p, i64, i64, c_i32p]),
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
     "gnna_launch_count": (i64, [i32]),

@@ -92,6 +92,7 @@ __device__ __forceinline__ void store_or_red(float *p, const float (&a)[V], bool
 enum : int {
     F_SCALE = 1,      // multiply the group sum by `scale` before the merge (GIN: eps, kernel.cu:686)
     F_ROWSCALE = 2,   // multiply the group sum by degrees[src] (GCN on pre-scaled features, see prescale_rows)
+    F_ACCUMULATE = 4, // `out` already holds partial sums (edges split over several CSRs): never a plain store
 };
 
 template <typename T, int VEC, int LPR, int KCH, bool WEIGHTED>
@@ -177,7 +178,7 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
 
     if (len > 0) {
         // plain store when this group is the node's whole adjacency list, else vector reduction
-        const bool own = (beg == __ldg(row_ptr + src)) && (end == __ldg(row_ptr + src + 1));
+        const bool own = !(flags & F_ACCUMULATE) && (beg == __ldg(row_ptr + src)) && (end == __ldg(row_ptr + src + 1));
         float mul = (flags & F_SCALE) ? scale : 1.f;
         if (flags & F_ROWSCALE) mul = __ldg(degrees + src);
         float *orow = out + (long long)src * dim;
@@ -394,7 +395,8 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
               const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
               const int32_t *part_ptr, const int32_t *part2node,
               int64_t num_nodes, int dim, int64_t num_parts,
-              int part_size, int dim_worker, int warp_per_block, cudaStream_t stream, int ldx, int64_t num_rows_x)
+              int part_size, int dim_worker, int warp_per_block, cudaStream_t stream, int ldx, int64_t num_rows_x,
+              bool accumulate)
 {
     (void)part_size;  // group length is read from part_ptr; any table with sorted groups works
     GNNA_REQUIRE(mode >= MODE_SAG && mode <= MODE_GCN_PRESCALED, "aggregate: bad mode %d", mode);
@@ -443,7 +445,7 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     }
 
     // rows shared by several groups are merged with reductions, rows without neighbours stay zero
-    {
+    if (!accumulate) {
         cudaError_t me = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)num_nodes * (size_t)dim, stream);
         if (me != cudaSuccess) { release(); return fail(GNNA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(me)); }
     }
@@ -458,6 +460,7 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     int flags = 0;
     if (mode == MODE_GIN) flags |= F_SCALE;
     if (mode == MODE_GCN_PRESCALED) flags |= F_ROWSCALE;
+    if (accumulate) flags |= F_ACCUMULATE;
     const bool weighted = (mode == MODE_GCN);
     float *o = reinterpret_cast<float *>(out);
     cudaError_t e;

@@ -34,7 +34,7 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
               const int32_t *part_ptr, const int32_t *part2node,
               int64_t num_nodes, int dim, int64_t num_parts,
               int part_size, int dim_worker, int warp_per_block, cudaStream_t stream,
-              int ldx = 0, int64_t num_rows_x = 0);
+              int ldx = 0, int64_t num_rows_x = 0, bool accumulate = false);
 
 bool gcn_exact_mode();   // GNNA_GCN_EXACT / gnna_set_gcn_exact
 

@@ -11,6 +11,7 @@
 // read it (ack counters, also in peer memory), so no rank can run more than one step ahead.
 // All waits are bounded (about 4 s of GPU clock) and report through an error word instead of hanging.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -18,20 +19,24 @@ namespace gnna {
 
 constexpr int MAX_PEERS = 16;
 constexpr int PUSH_WARPS = 8;
-constexpr int PUSH_ROWS_PER_CTA = 64;
+constexpr int PUSH_ROWS_PER_CTA = 128;
 constexpr long long SPIN_LIMIT_CYCLES = 8000000000LL;   // ~4 s at 2 GHz
 
+// Indexed by SLOT, not rank: slot s serves peer (my_rank + 1 + s) % world; the kernel feeds my peers in ring
+// order, so every receiver sees its chunks arrive one after the other -- which is what lets it start
+// aggregating a peer's rows while the others are still in flight.
 struct HaloPushParams {
-    float *peer_base[MAX_PEERS];          // peer p's feature buffer for this step parity (mapped)
-    unsigned *peer_flag[MAX_PEERS];       // &flags[my_rank] inside peer p's control block
-    const unsigned *ack_from[MAX_PEERS];  // &acks[p] inside MY control block (written by peer p)
-    long long dst_row0[MAX_PEERS];        // row of peer p's buffer where my block of rows starts
-    int send_begin[MAX_PEERS + 1];        // my send list is send_idx[send_begin[p] .. send_begin[p+1])
-    int cta_begin[MAX_PEERS + 1];         // CTAs [cta_begin[p], cta_begin[p+1]) serve peer p
+    float *peer_base[MAX_PEERS];          // the peer's feature buffer for this step parity (mapped)
+    unsigned *peer_flag[MAX_PEERS];       // &flags[my_rank] inside the peer's control block
+    const unsigned *ack_from[MAX_PEERS];  // &acks[peer] inside MY control block (written by the peer)
+    long long dst_row0[MAX_PEERS];        // row of the peer's buffer where my block of rows starts
+    int send_lo[MAX_PEERS];               // my send list for the peer is send_idx[send_lo .. send_hi)
+    int send_hi[MAX_PEERS];
     unsigned *done_counter;               // [MAX_PEERS] local scratch, zero between launches
     unsigned *error_word;                 // local: set to non-zero when a wait timed out
-    int world, my_rank, dim;
-    unsigned step;                        // 1, 2, 3, ...
+    int slots, dim;
+    const unsigned *step_ptr;             // local control word holding the current step (1, 2, 3, ...): read on the
+                                          // device so that a captured CUDA graph can be replayed step after step
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
@@ -45,66 +50,86 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Persistent: a fixed, small number of CTAs (prm.ctas, about one per SM or fewer) so that the push leaves most
+// thread slots to the aggregation kernel running next to it.  All CTAs serve slot 0 first, then slot 1, ...:
+// the peers' flags go up one after the other.
 __global__ void __launch_bounds__(PUSH_WARPS * 32)
 halo_push_kernel(const float *__restrict__ x_local, const long long *__restrict__ send_idx, HaloPushParams prm)
 {
     __shared__ int s_ok;
-    int p = 0;
-    while (p + 1 < prm.world && (int)blockIdx.x >= prm.cta_begin[p + 1]) p++;
-    while (p < prm.world && prm.cta_begin[p + 1] == prm.cta_begin[p]) p++;   // skip peers without CTAs (myself)
-    const int chunk = blockIdx.x - prm.cta_begin[p];
-    const int ctas_p = prm.cta_begin[p + 1] - prm.cta_begin[p];
-
-    // the buffer of this parity was last read by peer p at step-2: wait for its acknowledgement
-    if (threadIdx.x == 0) {
-        int ok = 1;
-        if (prm.step > 2) {
-            const long long t0 = clock64();
-            while (ld_acquire_sys(prm.ack_from[p]) + 2 < prm.step) {
-                if (clock64() - t0 > SPIN_LIMIT_CYCLES) { ok = 0; atomicExch(prm.error_word, 1u); break; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned step = *reinterpret_cast<const volatile unsigned *>(prm.step_ptr);
+    for (int p = 0; p < prm.slots; p++) {                    // slot
+        // the buffer of this parity was last read by this peer at step-2: wait for its acknowledgement
+        if (threadIdx.x == 0) {
+            int ok = 1;
+            if (step > 2) {
+                const long long t0 = clock64();
+                while (ld_acquire_sys(prm.ack_from[p]) + 2 < step) {
+                    if (clock64() - t0 > SPIN_LIMIT_CYCLES) { ok = 0; atomicExch(prm.error_word, 1u); break; }
+                }
+            }
+            s_ok = ok;
+        }
+        __syncthreads();
+        if (s_ok) {
+            float *dst_base = prm.peer_base[p] + (prm.dst_row0[p] - prm.send_lo[p]) * (long long)prm.dim;
+            const int rows = prm.send_hi[p] - prm.send_lo[p];
+            const int chunks = (rows + PUSH_ROWS_PER_CTA - 1) / PUSH_ROWS_PER_CTA;
+            for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+                const int r0 = prm.send_lo[p] + chunk * PUSH_ROWS_PER_CTA;
+                const int r1 = min(r0 + PUSH_ROWS_PER_CTA, prm.send_hi[p]);
+                if ((prm.dim & 3) == 0) {
+                    // 128-bit copies; `lpr` lanes per row (power of two), 32/lpr rows per warp pass, 4 passes in flight
+                    const int c4 = prm.dim >> 2;
+                    int lpr = 1;
+                    while (lpr < c4 && lpr < 32) lpr <<= 1;
+                    const int rpw = 32 / lpr, sub = lane / lpr, l = lane % lpr;
+                    constexpr int UNROLL = 4;
+                    for (int r = r0 + warp * rpw + sub; r < r1; r += PUSH_WARPS * rpw * UNROLL) {
+                        for (int c = l; c < c4; c += lpr) {
+                            float4 v[UNROLL];
+#pragma unroll
+                            for (int u = 0; u < UNROLL; u++) {
+                                const int rr = r + u * PUSH_WARPS * rpw;
+                                if (rr < r1) v[u] = __ldg(reinterpret_cast<const float4 *>(x_local + send_idx[rr] * prm.dim) + c);
+                            }
+#pragma unroll
+                            for (int u = 0; u < UNROLL; u++) {
+                                const int rr = r + u * PUSH_WARPS * rpw;
+                                if (rr < r1) reinterpret_cast<float4 *>(dst_base + (long long)rr * prm.dim)[c] = v[u];
+                            }
+                        }
+                    }
+                } else {
+                    for (int r = r0 + warp; r < r1; r += PUSH_WARPS) {
+                        const float *src = x_local + send_idx[r] * prm.dim;
+                        float *dst = dst_base + (long long)r * prm.dim;
+                        for (int c = lane; c < prm.dim; c += 32) dst[c] = __ldg(src + c);
+                    }
+                }
             }
         }
-        s_ok = ok;
-    }
-    __syncthreads();
-
-    if (s_ok) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int r0 = prm.send_begin[p] + chunk * PUSH_ROWS_PER_CTA;
-        const int r1 = min(r0 + PUSH_ROWS_PER_CTA, prm.send_begin[p + 1]);
-        float *dst_base = prm.peer_base[p] + (prm.dst_row0[p] - prm.send_begin[p]) * (long long)prm.dim;
-        if ((prm.dim & 3) == 0) {
-            const int c4 = prm.dim >> 2;
-            for (int r = r0 + warp; r < r1; r += PUSH_WARPS) {
-                const float4 *src = reinterpret_cast<const float4 *>(x_local + send_idx[r] * prm.dim);
-                float4 *dst = reinterpret_cast<float4 *>(dst_base + (long long)r * prm.dim);
-                for (int c = lane; c < c4; c += 32) dst[c] = __ldg(src + c);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();                          // my CTA's remote stores are visible system-wide
+            const unsigned done = atomicAdd(prm.done_counter + p, 1u);
+            if (done == gridDim.x - 1) {                     // last CTA done with this peer: raise its flag
+                prm.done_counter[p] = 0;
+                __threadfence_system();
+                st_release_sys(prm.peer_flag[p], step);
             }
-        } else {
-            for (int r = r0 + warp; r < r1; r += PUSH_WARPS) {
-                const float *src = x_local + send_idx[r] * prm.dim;
-                float *dst = dst_base + (long long)r * prm.dim;
-                for (int c = lane; c < prm.dim; c += 32) dst[c] = __ldg(src + c);
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();                              // my CTA's remote stores are visible system-wide
-        const unsigned done = atomicAdd(prm.done_counter + p, 1u);
-        if (done == (unsigned)ctas_p - 1) {                  // last CTA serving peer p: raise the flag
-            prm.done_counter[p] = 0;
-            __threadfence_system();
-            st_release_sys(prm.peer_flag[p], prm.step);
         }
     }
 }
 
-// one thread per peer: wait until flags[q] reaches `step`
-__global__ void halo_wait_kernel(const unsigned *flags, int world, int my_rank, unsigned step, unsigned *error_word)
+// one thread per peer: wait until flags[q] reaches `step` (only the peers in `peer_mask`)
+__global__ void halo_wait_kernel(const unsigned *flags, int world, int my_rank, unsigned peer_mask, const unsigned *step_ptr,
+                                 unsigned *error_word)
 {
     const int q = threadIdx.x;
-    if (q >= world || q == my_rank) return;
+    if (q >= world || q == my_rank || !((peer_mask >> q) & 1u)) return;
+    const unsigned step = *reinterpret_cast<const volatile unsigned *>(step_ptr);
     const long long t0 = clock64();
     while (ld_acquire_sys(flags + q) < step) {
         if (clock64() - t0 > SPIN_LIMIT_CYCLES) { atomicExch(error_word, 2u); break; }
@@ -114,7 +139,7 @@ __global__ void halo_wait_kernel(const unsigned *flags, int world, int my_rank, 
 struct HaloAckParams {
     unsigned *peer_ack[MAX_PEERS];   // &acks[my_rank] inside peer p's control block
     int world, my_rank;
-    unsigned step;
+    const unsigned *step_ptr;
 };
 
 // after the aggregation that consumed step `step`: tell every producer its buffer may be reused
@@ -123,8 +148,11 @@ __global__ void halo_ack_kernel(HaloAckParams prm)
     const int p = threadIdx.x;
     if (p >= prm.world || p == prm.my_rank) return;
     __threadfence_system();
-    st_release_sys(prm.peer_ack[p], prm.step);
+    st_release_sys(prm.peer_ack[p], *reinterpret_cast<const volatile unsigned *>(prm.step_ptr));
 }
+
+// first kernel of a step on the compute stream: step += 1 (everything else of the step is ordered after it)
+__global__ void halo_bump_kernel(unsigned *step_ptr) { *step_ptr = *step_ptr + 1; }
 
 }  // namespace gnna
 
@@ -166,62 +194,77 @@ extern "C" int gnna_ipc_free(void *ptr)
 
 // ---- one halo exchange step ------------------------------------------------------------------
 // control block layout (uint32, in IPC memory of every rank): [0..15] flags (written by producers),
-// [16..31] acks (written by consumers), [32..47] done counters (local), [48] error word (local)
+// [16..31] acks (written by consumers), [32..47] done counters (local), [48] error word (local),
+// [49] current step (local; incremented by gnna_halo_begin_step, read by push / wait / ack on the device)
 extern "C" int gnna_halo_push_f32(const float *x_local, const int64_t *send_idx, const int32_t *send_begin_host,
                                   void *const *peer_feature_base_host, void *const *peer_ctrl_host,
                                   const int64_t *peer_dst_row0_host, void *my_ctrl,
-                                  int world, int my_rank, int dim, uint32_t step, void *stream)
+                                  int world, int my_rank, int dim, void *stream)
 {
     GNNA_REQUIRE(world >= 1 && world <= MAX_PEERS && my_rank >= 0 && my_rank < world, "halo_push: bad world/rank");
-    GNNA_REQUIRE(dim > 0 && step >= 1, "halo_push: bad dim/step");
+    GNNA_REQUIRE(dim > 0, "halo_push: bad dim");
     if (world == 1) return GNNA_OK;
     GNNA_REQUIRE(x_local && send_begin_host && peer_feature_base_host && peer_ctrl_host && peer_dst_row0_host && my_ctrl,
                  "halo_push: null pointer");
     HaloPushParams prm;
     memset(&prm, 0, sizeof(prm));
     unsigned *ctrl = (unsigned *)my_ctrl;
-    int ctas = 0;
-    for (int p = 0; p < world; p++) {
-        prm.send_begin[p] = send_begin_host[p];
-        prm.cta_begin[p] = ctas;
-        if (p != my_rank) {
-            const int rows = send_begin_host[p + 1] - send_begin_host[p];
-            ctas += rows > 0 ? (rows + PUSH_ROWS_PER_CTA - 1) / PUSH_ROWS_PER_CTA : 1;   // >= 1: it raises the flag
-            prm.peer_base[p] = (float *)peer_feature_base_host[p];
-            prm.peer_flag[p] = (unsigned *)peer_ctrl_host[p] + my_rank;
-            prm.ack_from[p] = ctrl + 16 + p;
-            prm.dst_row0[p] = peer_dst_row0_host[p];
-        }
+    int max_chunks = 1;
+    for (int sl = 0; sl < world - 1; sl++) {
+        const int p = (my_rank + 1 + sl) % world;
+        const int rows = send_begin_host[p + 1] - send_begin_host[p];
+        const int chunks = (rows + PUSH_ROWS_PER_CTA - 1) / PUSH_ROWS_PER_CTA;
+        if (chunks > max_chunks) max_chunks = chunks;
+        prm.send_lo[sl] = send_begin_host[p];
+        prm.send_hi[sl] = send_begin_host[p + 1];
+        prm.peer_base[sl] = (float *)peer_feature_base_host[p];
+        prm.peer_flag[sl] = (unsigned *)peer_ctrl_host[p] + my_rank;
+        prm.ack_from[sl] = ctrl + 16 + p;
+        prm.dst_row0[sl] = peer_dst_row0_host[p];
     }
-    prm.send_begin[world] = send_begin_host[world];
-    prm.cta_begin[world] = ctas;
+    static int push_ctas = 0;
+    if (push_ctas == 0) {
+        const char *e = getenv("GNNA_PUSH_CTAS");
+        push_ctas = e ? atoi(e) : 0;
+        if (push_ctas <= 0) push_ctas = 96;        // < 148 SMs x 8 resident: most thread slots stay free for the aggregation
+    }
+    const int ctas = push_ctas < max_chunks ? push_ctas : max_chunks;
     GNNA_REQUIRE(send_idx || send_begin_host[world] == 0, "halo_push: null send_idx");
     prm.done_counter = ctrl + 32;
     prm.error_word = ctrl + 48;
-    prm.world = world;
-    prm.my_rank = my_rank;
+    prm.slots = world - 1;
     prm.dim = dim;
-    prm.step = step;
+    prm.step_ptr = ctrl + 49;
     halo_push_kernel<<<ctas, PUSH_WARPS * 32, 0, (cudaStream_t)stream>>>(x_local, (const long long *)send_idx, prm);
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
     return GNNA_OK;
 }
 
-extern "C" int gnna_halo_wait(void *my_ctrl, int world, int my_rank, uint32_t step, void *stream)
+extern "C" int gnna_halo_begin_step(void *my_ctrl, void *stream)
 {
-    GNNA_REQUIRE(my_ctrl && world >= 1 && world <= MAX_PEERS, "halo_wait: bad argument");
-    if (world == 1) return GNNA_OK;
-    unsigned *ctrl = (unsigned *)my_ctrl;
-    halo_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ctrl, world, my_rank, step, ctrl + 48);
+    GNNA_REQUIRE(my_ctrl, "halo_begin_step: null control block");
+    halo_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned *)my_ctrl + 49);
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
     return GNNA_OK;
 }
 
-extern "C" int gnna_halo_ack(void *const *peer_ctrl_host, int world, int my_rank, uint32_t step, void *stream)
+extern "C" int gnna_halo_wait(void *my_ctrl, int world, int my_rank, uint32_t peer_mask, void *stream)
 {
-    GNNA_REQUIRE(peer_ctrl_host && world >= 1 && world <= MAX_PEERS, "halo_ack: bad argument");
+    GNNA_REQUIRE(my_ctrl && world >= 1 && world <= MAX_PEERS, "halo_wait: bad argument");
+    if (world == 1) return GNNA_OK;
+    unsigned *ctrl = (unsigned *)my_ctrl;
+    if (peer_mask == 0) peer_mask = 0xffffffffu;
+    halo_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ctrl, world, my_rank, peer_mask, ctrl + 49, ctrl + 48);
+    GNNA_CUDA_CHECK(cudaGetLastError());
+    count_launch(1);
+    return GNNA_OK;
+}
+
+extern "C" int gnna_halo_ack(void *const *peer_ctrl_host, void *my_ctrl, int world, int my_rank, void *stream)
+{
+    GNNA_REQUIRE(peer_ctrl_host && my_ctrl && world >= 1 && world <= MAX_PEERS, "halo_ack: bad argument");
     if (world == 1) return GNNA_OK;
     HaloAckParams prm;
     memset(&prm, 0, sizeof(prm));
@@ -229,7 +272,7 @@ extern "C" int gnna_halo_ack(void *const *peer_ctrl_host, int world, int my_rank
         if (p != my_rank) prm.peer_ack[p] = (unsigned *)peer_ctrl_host[p] + 16 + my_rank;
     prm.world = world;
     prm.my_rank = my_rank;
-    prm.step = step;
+    prm.step_ptr = (const unsigned *)my_ctrl + 49;
     halo_ack_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(prm);
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);

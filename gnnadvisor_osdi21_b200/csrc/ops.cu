@@ -136,6 +136,27 @@ extern "C" int gnna_aggregate_f32_ex(int mode, const float *X, int64_t num_src_r
                      num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream, dim, num_src_rows);
 }
 
+extern "C" int gnna_aggregate_part_f32_ex(int mode, int accumulate, const float *X, int64_t num_src_rows, float *out,
+                                          int64_t num_dst_rows, const int32_t *row_ptr, const int32_t *col_idx,
+                                          const float *degrees, float eps, const int32_t *part_ptr,
+                                          const int32_t *part2node, int dim, int64_t num_parts,
+                                          int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    GNNA_REQUIRE(mode == MODE_SAG || mode == MODE_GIN || mode == MODE_GCN_PRESCALED,
+                 "gnna_aggregate_part_f32_ex: mode %d not supported (0, 2, 3)", mode);
+    GNNA_REQUIRE(dim % 4 == 0 && (((uintptr_t)X | (uintptr_t)out) & 15) == 0, "gnna_aggregate_part_f32_ex: dim %% 4 != 0 or unaligned");
+    return aggregate(mode, 4, X, out, row_ptr, col_idx, degrees, eps, part_ptr, part2node, num_dst_rows, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream, dim, num_src_rows,
+                     accumulate != 0);
+}
+
+extern "C" int gnna_prescale_rows_f32(const float *X, float *Xs, const float *degrees, int64_t num_rows, int dim, void *stream)
+{
+    GNNA_REQUIRE(num_rows >= 0 && dim >= 0, "gnna_prescale_rows_f32: negative size");
+    GNNA_REQUIRE(num_rows == 0 || dim == 0 || (X && Xs && degrees), "gnna_prescale_rows_f32: null pointer");
+    return prescale_rows(X, Xs, degrees, num_rows, dim, (cudaStream_t)stream);
+}
+
 #define GNNA_TRY(expr)             \
     do {                           \
         int _rc = (expr);          \

@@ -24,10 +24,21 @@ import torch
 import torch.distributed as dist
 
 
-def partition_ranges(row_ptr, world):
-    """Vertex boundaries v[0..world] with ~equal edge counts: v_g = first row whose offset >= g*E/world."""
+def default_row_weight(world):
+    """Cost of owning one row, in edge-equivalents, when cutting the vertex ranges.  A rank's step is
+    aggregation (proportional to its edges) plus halo traffic (every peer needs most of its rows on dense graphs:
+    proportional to rows * (world-1)).  Measured on 8xB200 (Reddit look-alike, D=64): 0.0154 ns per edge against
+    ~4 ns per row at 7 peers, i.e. ~40 edge-equivalents per row and peer."""
+    return 0 if world <= 1 else 40 * (world - 1)
+
+
+def partition_ranges(row_ptr, world, row_weight=0):
+    """Vertex boundaries v[0..world] with ~equal cost: cost(rows [a,b)) = edges + row_weight * (b-a).
+    row_weight = 0 balances edges only: v_g = first row whose offset >= g*E/world."""
     rp = row_ptr.to(torch.int64)
     n = rp.numel() - 1
+    if row_weight:
+        rp = rp + int(row_weight) * torch.arange(n + 1, dtype=torch.int64, device=rp.device)
     E = int(rp[-1])
     targets = torch.tensor([(E * g) // world for g in range(world + 1)], dtype=torch.int64, device=rp.device)
     v = torch.searchsorted(rp, targets, right=False).clamp_(0, n)
@@ -65,14 +76,14 @@ def _a2a(out, inp, out_splits, in_splits, group):
 class ShardedGraph:
     """This rank's shard of a graph every rank can see (replicated CSR in, sharded tables out)."""
 
-    def __init__(self, row_ptr, col_idx, part_size, device=None, group=None, ranges=None):
+    def __init__(self, row_ptr, col_idx, part_size, device=None, group=None, ranges=None, row_weight=0):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         device = torch.device(device) if device is not None else row_ptr.device
         self.device = device
         self.part_size = int(part_size)
-        self.ranges = ranges if ranges is not None else partition_ranges(row_ptr, self.world)
+        self.ranges = ranges if ranges is not None else partition_ranges(row_ptr, self.world, row_weight)
         v0, v1 = self.ranges[self.rank], self.ranges[self.rank + 1]
         self.v0, self.n_local = v0, v1 - v0
         self.num_nodes_global = row_ptr.numel() - 1
@@ -138,6 +149,79 @@ class ShardedGraph:
         send = x_ext[:self.n_local].index_select(0, self.send_idx)
         _a2a(x_ext[self.n_local:], send, self.recv_counts, self.send_counts, self.group)
         return x_ext
+
+    # -------------------------------------------------------------------------------- overlap: per-owner sub-shards
+    def build_owner_shards(self):
+        """Split this rank's CSR by the OWNER of the neighbour: one sub-CSR (+ group table) per rank, listed in the
+        order their rows arrive (own rows first, then rank-1, rank-2, ...: every sender serves its peers in ring
+        order).  The overlapped step aggregates a sub-shard as soon as its owner's rows have landed while the
+        remaining rows are still crossing NVLink."""
+        from . import ops
+        rank, world, n_local, dev = self.rank, self.world, self.n_local, self.device
+        hoff = [0]
+        for c in self.recv_counts:
+            hoff.append(hoff[-1] + c)
+        hoff_t = torch.tensor(hoff, dtype=torch.int64, device=dev)
+        cols = self.col_idx.to(torch.int64)
+        deg_rows = (self.row_ptr[1:] - self.row_ptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(n_local, device=dev), deg_rows)
+        owner = torch.where(cols < n_local, torch.full_like(cols, rank),
+                            torch.searchsorted(hoff_t, (cols - n_local).clamp_min(0), right=True) - 1)
+        self.owner_order = [(rank - k) % world for k in range(world)]
+        self.owner_shards = []
+        for q in self.owner_order:
+            m = owner == q
+            rp = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+            rp[1:] = torch.cumsum(torch.bincount(rows[m], minlength=n_local), 0)
+            rp = rp.to(torch.int32).contiguous()
+            ci = cols[m].to(torch.int32).contiguous()
+            pp, pn = ops.build_part_exact(self.part_size, rp)
+            self.owner_shards.append((rp, ci, pp, pn))
+        return self
+
+    def write_local(self, peer, x_local, prescale):
+        """Fill the local rows of the next step's feature buffer from x_local [n_local, D] (scaled by the GCN
+        degrees when `prescale`): what a layer's producer (the X*W epilogue) does in a real pipeline."""
+        from . import _lib
+        dst = self.local(peer.features())
+        if prescale:
+            p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
+            _lib.check(_lib.load().gnna_prescale_rows_f32(p(x_local), p(dst), p(self.degrees_ext), self.n_local, x_local.shape[1],
+                                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "prescale")
+        else:
+            dst.copy_(x_local)
+        return dst
+
+    def aggregate_overlapped(self, mode, peer, out, eps=0.5, dim_worker=32, warp_per_block=4):
+        """One sharded step with the exchange hidden behind the aggregation.  The next step's buffer
+        (peer.features()) must hold this rank's rows -- pre-scaled by degrees for mode 1, see write_local.
+        mode: 0 SAG, 1 GCN, 2 GIN."""
+        from . import _lib
+        assert self._tables_built and getattr(self, "owner_shards", None), "call build_tables() and build_owner_shards() first"
+        lib = _lib.load()
+        cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_comm_stream"):
+            self._comm_stream = torch.cuda.Stream(self.device, priority=-1)
+            self._ev_ready, self._ev_pushed = torch.cuda.Event(), torch.cuda.Event()
+        peer.begin_step()
+        self._ev_ready.record(cur)
+        self._comm_stream.wait_event(self._ev_ready)              # my rows are in the buffer, the step is advanced
+        x_ext = peer.push(self._comm_stream)
+        self._ev_pushed.record(self._comm_stream)
+        d = x_ext.shape[1]
+        kmode = 3 if mode == 1 else mode
+        p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
+        st = ctypes.c_void_p(cur.cuda_stream)
+        for k, (q, (rp, ci, pp, pn)) in enumerate(zip(self.owner_order, self.owner_shards)):
+            if q != self.rank:
+                peer.wait([q], cur)
+            _lib.check(lib.gnna_aggregate_part_f32_ex(kmode, 0 if k == 0 else 1, p(x_ext), self.n_ext, p(out), self.n_local,
+                                                      p(rp), p(ci), p(self.degrees_ext) if kmode == 3 else ctypes.c_void_p(0),
+                                                      float(eps), p(pp), p(pn), d, pn.numel(),
+                                                      self.part_size, int(dim_worker), int(warp_per_block), st), "overlapped aggregate")
+        peer.ack()
+        cur.wait_event(self._ev_pushed)                           # the push has read my rows: the buffer may be refilled
+        return out
 
     def halo_bytes(self, dim, elem=4):
         return {"recv": self.n_halo * dim * elem, "send": int(self.send_idx.numel()) * dim * elem}
@@ -255,25 +339,48 @@ class PeerHalo:
         s = self.step + 1 if step is None else step
         return self.bufs[s & 1]
 
-    def exchange(self):
-        """Push my rows into my peers' halo rows for the next step and wait for theirs (on the current stream)."""
+    def begin_step(self):
+        """First call of a step, on the compute (current) stream: advances the step counter on the device.
+        Returns the step's feature buffer."""
+        from . import _lib
+        self.step += 1
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self.lib.gnna_halo_begin_step(ctypes.c_void_p(self.ctrl_ptr), st), "halo_begin_step")
+        return self.bufs[self.step & 1]
+
+    def push(self, stream=None):
+        """Store my rows into my peers' halo rows (ring order) on `stream`, which must be ordered after begin_step."""
         from . import _lib
         sg = self.sg
-        self.step += 1
         b = self.step & 1
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
         _lib.check(self.lib.gnna_halo_push_f32(ctypes.c_void_p(self.buf_ptr[b]),
                                                ctypes.c_void_p(sg.send_idx.data_ptr() if sg.send_idx.numel() else 0),
                                                self.send_begin, self.c_peer_buf[b], self.c_peer_ctrl, self.c_dst_row0,
-                                               ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.dim, self.step, st), "halo_push")
-        _lib.check(self.lib.gnna_halo_wait(ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.step, st), "halo_wait")
+                                               ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.dim, st), "halo_push")
         return self.bufs[b]
+
+    def wait(self, peers=None, stream=None):
+        """Make `stream` wait until the rows of `peers` (ranks; None = all) for the current step have landed."""
+        from . import _lib
+        mask = 0
+        for q in (peers or []):
+            mask |= 1 << q
+        st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        _lib.check(self.lib.gnna_halo_wait(ctypes.c_void_p(self.ctrl_ptr), self.sg.world, self.sg.rank, mask, st), "halo_wait")
+
+    def exchange(self):
+        """Push my rows into my peers' halo rows for the next step and wait for theirs (on the current stream)."""
+        self.begin_step()
+        buf = self.push()
+        self.wait()
+        return buf
 
     def ack(self):
         """After the aggregation of the current step: producers may overwrite this parity again."""
         from . import _lib
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(self.lib.gnna_halo_ack(self.c_peer_ctrl, self.sg.world, self.sg.rank, self.step, st), "halo_ack")
+        _lib.check(self.lib.gnna_halo_ack(self.c_peer_ctrl, ctypes.c_void_p(self.ctrl_ptr), self.sg.world, self.sg.rank, st), "halo_ack")
 
     def error(self):
         """Non-zero if a bounded wait inside a kernel timed out (1: ack wait, 2: flag wait). Synchronises."""

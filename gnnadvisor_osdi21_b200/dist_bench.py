@@ -33,7 +33,8 @@ def run(args, bench):
     gr = graph.lookalike(args.workload, device=device, scale=args.scale)
     rp, ci = gr["row_ptr"], gr["col_idx"]
     N, E, D = gr["num_nodes"], ci.numel(), args.dim
-    sg = gdist.ShardedGraph(rp, ci, args.part_size, device=device).build_tables()
+    row_weight = int(os.environ.get("GNNA_ROW_WEIGHT", gdist.default_row_weight(world)))
+    sg = gdist.ShardedGraph(rp, ci, args.part_size, device=device, row_weight=row_weight).build_tables()
     gen = torch.Generator(device=device).manual_seed(20212)
     X = torch.randn(N, D, device=device, generator=gen)
     x_ext = sg.new_features(D)
@@ -60,15 +61,67 @@ def run(args, bench):
         peer = None
         halo_mode = "nccl all_to_all_single (peer mapping failed on another rank)"
 
-    def step():
+    def step_serial():
         sg.aggregate(1, x_ext, out=out, dim_worker=args.dim_worker, warp_per_block=args.warp_per_block, peer=peer)
 
-    halo_check = None
+    # overlapped step: the rank's rows are written pre-scaled into the step buffer (what the X*W epilogue of a
+    # layer would do), the push runs on a second stream, per-owner sub-shards are aggregated as their rows land
+    overlap = peer is not None and D % 4 == 0 and os.environ.get("GNNA_OVERLAP", "1") == "1"
+    x_src = sg.local(x_ext).clone() if overlap else None
+    if overlap:
+        sg.build_owner_shards()
+
+    def step_overlap():
+        sg.write_local(peer, x_src, prescale=True)
+        sg.aggregate_overlapped(1, peer, out, dim_worker=args.dim_worker, warp_per_block=args.warp_per_block)
+
+    step = step_overlap if overlap else step_serial
+
+    # the overlapped step is ~12 small launches on two streams: replay it from CUDA graphs (one per buffer
+    # parity; the step counter lives in device memory) so the host is not the bottleneck at 8 GPUs
+    graphs, launches_per_step = None, None
+    if overlap and os.environ.get("GNNA_GRAPH", "1") == "1":
+        try:
+            for _ in range(3):
+                step_overlap()
+            torch.cuda.synchronize()
+            dist.barrier(device_ids=[local])
+            base_step = peer.step
+            graphs = []
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                c0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    step_overlap()
+                launches_per_step = _lib.launch_count() - c0
+                graphs.append(g)
+            peer.step = base_step                       # nothing ran during capture
+            state = {"i": 0}
+
+            def step_graph():
+                graphs[state["i"] & 1].replay()
+                state["i"] += 1
+                peer.step += 1
+            step = step_graph
+        except Exception as e:   # noqa: BLE001
+            graphs = None
+            halo_mode += " (graph capture failed: %s)" % str(e)[:60]
+            step = step_overlap
+
+    halo_check, halo_diff_elems = None, None
     if peer is not None:   # the two exchange implementations must give the same aggregation
         ref_out = sg.aggregate(1, x_ext, dim_worker=args.dim_worker, warp_per_block=args.warp_per_block).clone()
+        step_serial()
+        step()
         step()
         step()
         halo_check = ((out - ref_out).abs().max() / ref_out.abs().max().clamp_min(1e-30)).item()
+        halo_diff_elems = int((out != ref_out).sum().item())
+        out.zero_()                                    # and once more from a zeroed output: the step must rewrite it
+        step()
+        torch.cuda.synchronize()
+        halo_check = max(halo_check, ((out - ref_out).abs().max() / ref_out.abs().max().clamp_min(1e-30)).item())
+        assert halo_check < 1e-4, "overlapped / peer exchange disagrees with the NCCL path: %g" % halo_check
 
     def kernel_only():
         sg.aggregate(1, x_ext, out=out, dim_worker=args.dim_worker, warp_per_block=args.warp_per_block, do_exchange=False)
@@ -94,9 +147,12 @@ def run(args, bench):
     ms = reduce_max(bench.timed(step, args.steps, args.warmup, barrier)) / args.steps
     clocks = sampler.stop() if sampler else None
     launches = _lib.launch_count() * args.steps // (args.steps + args.warmup)
+    if graphs is not None:
+        launches = launches_per_step * args.steps
     k = max(3, args.steps // 4)
     ms_kernel = reduce_max(bench.timed(kernel_only, k, 3, barrier)) / k
     ms_exch = reduce_max(bench.timed(exchange_only, k, 3, barrier)) / k
+    ms_serial = reduce_max(bench.timed(step_serial, k, 3, barrier)) / k if overlap else ms
 
     # end to end: this rank's features start and end in pinned host memory
     x_host = sg.local(x_ext).cpu().pin_memory()
@@ -126,8 +182,8 @@ def run(args, bench):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": bench.config_of(args, N, E, int(sum(s[3] for s in per_rank)),
-                                          {"parallelism": "1-D vertex-range shards x%d (edge-balanced), one halo exchange per step" % world,
-                                           "halo_exchange": halo_mode}),
+                                          {"parallelism": "1-D vertex-range shards x%d (cost-balanced: edges + %d per row), one halo exchange per step" % (world, row_weight),
+                                           "halo_exchange": halo_mode + ("; per-owner sub-shards aggregated while the rest is in flight" if overlap else "")}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "gnna::aggregate_kernel<float,4,16,1,false> on the most loaded shard",
                              "alg_bytes_per_launch": B, "peak_source": peak_src,
@@ -136,8 +192,9 @@ def run(args, bench):
                         "h2d_bytes_per_step": int(sum(s[1] for s in per_rank) * D * 4),
                         "d2h_bytes_per_step": int(sum(s[1] for s in per_rank) * D * 4)},
                 "gpu_launches": int(launches), "clocks": clocks, "impl": "ours",
-                "extras": {"ms_kernel_only": ms_kernel, "ms_exchange_only": ms_exch,
-                           "peer_vs_nccl_max_rel_diff": halo_check,
+                "extras": {"ms_kernel_only": ms_kernel, "ms_exchange_only": ms_exch, "ms_step_without_overlap": ms_serial,
+                           "overlap": bool(overlap), "cuda_graph": graphs is not None,
+                           "peer_vs_nccl_max_rel_diff": halo_check, "peer_vs_nccl_differing_elements": halo_diff_elems,
                            "shards": [{"edges": int(s[0]), "rows": int(s[1]), "halo_rows": int(s[2]),
                                        "halo_recv_bytes": int(s[4]), "halo_send_bytes": int(s[5])} for s in per_rank]}}
         sys.stdout.flush()

@@ -108,6 +108,19 @@ GNNA_API int gnna_aggregate_f32_ex(int mode, const float *X, int64_t num_src_row
                                    const int32_t *part_ptr, const int32_t *part2node, int dim, int64_t num_parts,
                                    int part_size, int dim_worker, int warp_per_block, void *stream);
 
+/* Same, for a graph whose edges are split over several CSRs (per-owner sub-shards of the overlapped
+ * multi-GPU step): accumulate != 0 ADDS into `out` (no zero fill, always reductions).  mode 3 = GCN on
+ * features already scaled by degrees[j] (gnna_prescale_rows_f32); requires dim % 4 == 0.             */
+GNNA_API int gnna_aggregate_part_f32_ex(int mode, int accumulate, const float *X, int64_t num_src_rows, float *out,
+                                        int64_t num_dst_rows, const int32_t *row_ptr, const int32_t *col_idx,
+                                        const float *degrees, float eps, const int32_t *part_ptr,
+                                        const int32_t *part2node, int dim, int64_t num_parts,
+                                        int part_size, int dim_worker, int warp_per_block, void *stream);
+
+/* Xs[i,:] = degrees[i] * X[i,:] (X == Xs allowed): the pre-scale pass of the default GCN path, exposed
+ * so a producer can hand pre-scaled rows to gnna_aggregate_part_f32_ex(mode 3) / the halo push.          */
+GNNA_API int gnna_prescale_rows_f32(const float *X, float *Xs, const float *degrees, int64_t num_rows, int dim, void *stream);
+
 /* bf16-storage variant: neighbour rows are gathered as bf16 (half the gather bytes), summed in
  * fp32 and written as fp32.  An extension: the reference is fp32-only.
  * mode: 0 = SAG, 1 = GCN (degrees, per-edge weights), 2 = GIN (eps), 3 = GCN on features the caller
@@ -179,20 +192,26 @@ GNNA_API int gnna_ipc_open(const unsigned char *handle64, void **ptr);
 GNNA_API int gnna_ipc_close(void *ptr);
 GNNA_API int gnna_ipc_free(void *ptr);
 
-/* One exchange step.  push: ONE kernel copies, for every peer p, rows x_local[send_idx[send_begin[p] ..
- * send_begin[p+1])] into rows peer_dst_row0[p].. of peer p's mapped feature buffer (128-bit stores over
- * NVLink) and then stores `step` into flags[my_rank] of p's control block (release, system scope).
- * wait: returns (on the stream) once every peer's flag in MY control block reached `step`.
- * ack: after the aggregation that read the halo rows, stores `step` into acks[my_rank] of every peer so
- * the buffer of this step parity may be overwritten at step+2 (push waits for it).  Control block:
- * 64 uint32 in IPC memory: [0,16) flags, [16,32) acks, [32,48) scratch, [48] error word (non-zero:
- * a bounded wait timed out).  step counts 1, 2, 3, ...; *_host arrays have `world` entries.          */
+/* One exchange step = begin_step, push, wait, (aggregate), ack.  The step number (1, 2, 3, ...) lives in the
+ * control block and is read on the device, so a step captured in a CUDA graph can be replayed.
+ * begin_step: first thing on the compute stream: step += 1.
+ * push: ONE persistent kernel (GNNA_PUSH_CTAS CTAs, default 96) copies, peer after peer in ring order
+ * (my_rank+1, my_rank+2, ...), rows x_local[send_idx[send_begin[p] .. send_begin[p+1])] into rows
+ * peer_dst_row0[p].. of peer p's mapped feature buffer (128-bit stores over NVLink) and then stores the step
+ * into flags[my_rank] of p's control block (release, system scope).  Must be ordered after begin_step.
+ * wait: returns (on the stream) once the flag of every peer in `peer_mask` (bit q = rank q; 0 = all peers)
+ * in MY control block reached the step.
+ * ack: after the aggregation that read the halo rows: stores the step into acks[my_rank] of every peer, so
+ * the buffer of this step parity may be overwritten at step+2 (push waits for it).
+ * Control block: 64 uint32 in IPC memory: [0,16) flags, [16,32) acks, [32,48) scratch, [48] error word
+ * (non-zero: a bounded wait timed out), [49] step.  *_host arrays have `world` entries.              */
+GNNA_API int gnna_halo_begin_step(void *my_ctrl, void *stream);
 GNNA_API int gnna_halo_push_f32(const float *x_local, const int64_t *send_idx, const int32_t *send_begin_host,
                                 void *const *peer_feature_base_host, void *const *peer_ctrl_host,
                                 const int64_t *peer_dst_row0_host, void *my_ctrl,
-                                int world, int my_rank, int dim, uint32_t step, void *stream);
-GNNA_API int gnna_halo_wait(void *my_ctrl, int world, int my_rank, uint32_t step, void *stream);
-GNNA_API int gnna_halo_ack(void *const *peer_ctrl_host, int world, int my_rank, uint32_t step, void *stream);
+                                int world, int my_rank, int dim, void *stream);
+GNNA_API int gnna_halo_wait(void *my_ctrl, int world, int my_rank, uint32_t peer_mask, void *stream);
+GNNA_API int gnna_halo_ack(void *const *peer_ctrl_host, void *my_ctrl, int world, int my_rank, void *stream);
 
 /* ---- vertex reordering ----------------------------------------------------------------------
  * replaces the python module `rabbit` (rabbit_module/src/reorder.cpp:235-295, rabbit_order.hpp:393-673):

@@ -86,3 +86,9 @@ def test_partition_ranges_balance_edges_not_nodes():
     e = [int(rp[v[i + 1]] - rp[v[i]]) for i in range(4)]
     assert max(e) <= 10000 + 10 and v[1] - v[0] < 250
     assert gdist.partition_ranges(rp, 1) == [0, 1000]
+    # a per-row cost moves rows away from the ranks that hold many light rows
+    w = gdist.partition_ranges(rp, 4, row_weight=40)
+    assert w[0] == 0 and w[-1] == 1000 and w == sorted(w)
+    rows_e = [v[i + 1] - v[i] for i in range(4)]
+    rows_w = [w[i + 1] - w[i] for i in range(4)]
+    assert max(rows_w) < max(rows_e) and gdist.default_row_weight(1) == 0 and gdist.default_row_weight(8) == 280
