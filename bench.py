@@ -267,16 +267,21 @@ def run_single(args):
     peak, peak_src = peak_gbs()
     B = alg_bytes(E, N, D, P)
     achieved = B / (ms * 1e-3) / 1e9
-    traffic = None
+    traffic, l2_bytes = None, None
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.scale == 1.0:
         try:
-            traffic = json.load(open(tp)).get("%s_D%d_f32" % (args.workload, D))
+            prof = json.load(open(tp))
+            traffic = prof.get("%s_D%d_f32" % (args.workload, D))
+            l2_bytes = prof.get("%s_D%d_f32_l2_to_sm_bytes" % (args.workload, D))
         except Exception:   # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "gnna::aggregate_kernel<float,4,16,1,false> (+ prescale_rows_kernel<4>, 0.4% of the bytes)",
                 "alg_bytes_per_launch": B, "peak_source": peak_src,
+                "dram_GBs": (traffic / (ms * 1e-3) / 1e9) if traffic else None,
+                "dram_frac": (traffic / (ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "l2_to_sm_GBs": (l2_bytes / (ms * 1e-3) / 1e9) if l2_bytes else None,
                 "note": "step = cudaMemsetAsync(out) + prescale_rows + aggregate_kernel, timed together; features (%.0f MB) fit in L2, so "
                         "achieved may exceed the HBM copy peak -- see traffic (ncu dram bytes per launch)" % (N * D * 4 / 1e6)}
 

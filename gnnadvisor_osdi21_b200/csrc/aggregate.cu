@@ -274,13 +274,16 @@ static Geometry choose_geometry(int elem_bytes, int dim, long long num_parts, in
     if (dim_worker > 0) {
         int want = pow2_floor(dim_worker > 32 ? 32 : dim_worker);
         if (want < g.lpr) g.lpr = want;
-    }
+    } else if (need == 16) {
+        g.lpr = 8;          // library's own choice for 9..16 chunks per row (fp32 D = 36..64): two chunks per lane,
+    }                       // twice the groups in flight per warp -- 7 % faster when HBM-bound, equal when L2-bound
+                            // (profiles/r01_params_*.txt); wider rows were not measured that way and keep one chunk per lane
     int per_lane = (nchunks + g.lpr - 1) / g.lpr;
     const int max_kch = g.vec >= 8 ? 2 : 4;        // accumulators: KCH*VEC <= 16 registers
     g.kch = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
     if (g.kch > max_kch) g.kch = max_kch;
     g.gy = (nchunks + g.lpr * g.kch - 1) / (g.lpr * g.kch);
-    g.wpb = warp_per_block <= 0 ? 8 : (warp_per_block > GNNA_LB / 32 ? GNNA_LB / 32 : warp_per_block);
+    g.wpb = warp_per_block <= 0 ? 4 : (warp_per_block > GNNA_LB / 32 ? GNNA_LB / 32 : warp_per_block);
     const int S = 32 / g.lpr;
     const long long per_block = (long long)g.wpb * S;
     g.gx = (num_parts + per_block - 1) / per_block;

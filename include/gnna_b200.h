@@ -20,7 +20,8 @@
  *     exit(-1)s on a launch error, kernel.cu:177-181 -- we return the error instead)
  *   - part_size / dim_worker / warp_per_block keep the reference's meaning (param.py:27-29):
  *     neighbours per group / lanes that cooperate on one neighbour row / warps per CTA.
- *     dim_worker <= 0 or warp_per_block <= 0 selects the built-in B200 choice.
+ *     dim_worker <= 0 or warp_per_block <= 0 selects the built-in B200 choice (4 warps per CTA; one 16-byte
+ *     chunk per lane, two for rows of 9..16 chunks).
  *   - a group with part_ptr[w+1] <= part_ptr[w] contributes nothing (kernel.cu:383).
  */
 #ifndef GNNA_B200_H

@@ -455,3 +455,49 @@ def test_fused_tile_edge_cases():
     with pytest.raises(RuntimeError, match="no fused tile"):
         ops.aggregate_gemm_fused(2, dev(rand_features(300, 48, 3)), dev(rand_weight(48, 8, 4)), *g.gargs(), g.d_deg, 0.5,
                                  *g.pargs(), 32, 32, 8)
+
+
+# ------------------------------------------------------------------------------------------ split CSRs, host pipeline
+def test_aggregation_over_split_csrs_accumulates():
+    """gnna_aggregate_part_f32_ex: the edges of a graph split over two CSRs (by column range, as the sharded
+    path splits them by owner) and aggregated one after the other into the same output equal the whole graph."""
+    import ctypes
+    from gnnadvisor_osdi21_b200 import _lib
+    rp, ci = GRAPHS["rmat"]()
+    n = len(rp) - 1
+    g = G(rp, ci, 32)
+    X = rand_features(n, 64, 77)
+    rows = np.repeat(np.arange(n), rp[1:] - rp[:-1])
+    out = torch.empty(n, 64, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for mode in (0, 2, 3):
+        Xin = X * g.deg[:, None] if mode == 3 else X
+        dX = dev(Xin.astype(np.float32))
+        for k, mask in enumerate((ci < n // 3, ci >= n // 3)):
+            rp_k = np.concatenate([[0], np.cumsum(np.bincount(rows[mask], minlength=n))]).astype(np.int32)
+            ci_k = ci[mask]
+            pp_k, pn_k = oracle.build_part(32, rp_k, exact=True)
+            d_rp, d_ci, d_pp, d_pn = dev(rp_k), dev(ci_k), dev(pp_k), dev(pn_k)
+            _lib.check(_lib.load().gnna_aggregate_part_f32_ex(mode, k, p(dX), n, p(out), n, p(d_rp), p(d_ci),
+                                                              p(g.d_deg) if mode == 3 else ctypes.c_void_p(0), 0.5, p(d_pp), p(d_pn),
+                                                              64, d_pn.numel(), 32, 0, 0, st), "part")
+        ref_mode = 1 if mode == 3 else mode
+        assert_close(out.cpu().numpy(), oracle.aggregate(ref_mode, X, ci, g.deg, 0.5, g.pp, g.pn), what="split mode %d" % mode,
+                     terms=g.terms(ref_mode, X))
+
+
+def test_host_aggregator_pipeline():
+    """HostAggregator: pinned host in / out, three overlapped stages, several steps with different inputs."""
+    from gnnadvisor_osdi21_b200.host_pipeline import HostAggregator
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+    pipe = HostAggregator(g.d_rp, g.d_ci, g.d_deg, g.d_pp, g.d_pn, g.n, 32, mode=1)
+    xs = [torch.from_numpy(rand_features(g.n, 32, 900 + i)).pin_memory() for i in range(5)]
+    outs = [torch.empty(g.n, 32).pin_memory() for _ in range(5)]
+    for x, o in zip(xs, outs):
+        pipe.submit(x, o)
+    pipe.drain()
+    for x, o in zip(xs, outs):
+        assert_close(o.numpy(), oracle.aggregate(1, x.numpy(), ci, g.deg, 1.0, g.pp, g.pn), what="host pipeline",
+                     terms=g.terms(1, x.numpy()))
