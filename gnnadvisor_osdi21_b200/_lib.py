@@ -67,6 +67,7 @@ SIGNATURES = {
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
     "gnna_launch_count": (i64, [i32]),
     "gnna_set_gcn_exact": (i32, [i32]),
+    "gnna_set_staged": (i32, [i32]),
 }
 
 _lib = None
@@ -103,3 +104,8 @@ def launch_count(reset=False):
 def set_gcn_exact(on):
     """True: per-edge rounding of the reference (bit-identical single-group rows); False: pre-scaled (default)."""
     return bool(load().gnna_set_gcn_exact(1 if on else 0))
+
+
+def set_staged(on):
+    """True: TMA-staged persistent aggregation kernel where it applies (csrc/aggregate_staged.cu)."""
+    return bool(load().gnna_set_staged(1 if on else 0))

@@ -356,6 +356,16 @@ bool gcn_exact_mode()
 }
 
 // Xs[i, 0:dim] = (degrees ? degrees[i] : 1) * X[i, 0:dim]; columns dim..ldx-1 zero.  X == Xs allowed when ldx == dim.
+static int g_staged = -1;
+static bool staged_mode()
+{
+    if (g_staged < 0) {
+        const char *e = getenv("GNNA_STAGED");
+        g_staged = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_staged == 1;
+}
+
 int repack_rows(const float *X, float *Xs, const float *degrees, int64_t num_nodes, int dim, int ldx, cudaStream_t stream)
 {
     if (num_nodes == 0 || dim == 0) return GNNA_OK;
@@ -467,6 +477,16 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     const bool weighted = (mode == MODE_GCN);
     float *o = reinterpret_cast<float *>(out);
     cudaError_t e;
+    // opt-in: persistent kernel with the integer streams staged through TMA bulk copies (aggregate_staged.cu)
+    if (staged_mode() && elem_bytes == 4 && !weighted && ldx == dim && g.gy == 1) {
+        const int rc = aggregate_staged((const float *)X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
+                                        (long long)num_parts, 0x7fffffffffffffffLL, dim, part_size, scale, flags, stream);
+        if (rc != GNNA_ERR_UNSUPPORTED) {
+            e = cudaSuccess;
+            if (rc != GNNA_OK) { release(); return rc; }
+            goto finish;
+        }
+    }
     if (elem_bytes == 4) {
         if (weighted)
             e = dispatch_lpr<float, 4, true>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
@@ -482,6 +502,8 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
             e = dispatch_vec<__nv_bfloat16, false>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
                                                    (long long)num_parts, dim, ldx, scale, flags);
     }
+    count_launch(1);
+finish:
     if (e == cudaSuccess && out_scratch) {
         const long long total = (long long)num_nodes * out_dim;
         long long blocks = (total + 255) / 256;
@@ -492,11 +514,17 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     }
     release();
     if (e != cudaSuccess) return fail(GNNA_ERR_CUDA, "aggregate launch: %s", cudaGetErrorString(e));
-    count_launch(1);
     return GNNA_OK;
 }
 
 }  // namespace gnna
+
+extern "C" int gnna_set_staged(int on)
+{
+    const int prev = gnna::staged_mode() ? 1 : 0;
+    gnna::g_staged = on ? 1 : 0;
+    return prev;
+}
 
 extern "C" int gnna_set_gcn_exact(int on)
 {

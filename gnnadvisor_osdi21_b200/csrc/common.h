@@ -36,6 +36,11 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
               int part_size, int dim_worker, int warp_per_block, cudaStream_t stream,
               int ldx = 0, int64_t num_rows_x = 0, bool accumulate = false);
 
+// persistent TMA-staged variant (aggregate_staged.cu); GNNA_ERR_UNSUPPORTED when the shape has no such variant
+int aggregate_staged(const float *X, float *out, const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                     const int32_t *part_ptr, const int32_t *part2node, long long num_parts, long long num_edges,
+                     int dim, int part_size, float scale, int flags, cudaStream_t stream);
+
 bool gcn_exact_mode();   // GNNA_GCN_EXACT / gnna_set_gcn_exact
 
 // Xs[i,:] = degrees[i] * X[i,:]  (X == Xs allowed)

@@ -245,6 +245,13 @@ GNNA_API int gnna_query_launch(int elem_bytes, int dim, int64_t num_parts, int d
  * environment.  Returns the previous setting.                                                  */
 GNNA_API int gnna_set_gcn_exact(int on);
 
+/* 1 = use the persistent kernel that streams the group table and the column indices through TMA bulk copies
+ * (cp.async.bulk) into a shared-memory ring (csrc/aggregate_staged.cu) where it applies (fp32, dim % 4 == 0,
+ * 8 <= dim <= 128, part_size <= 64); 0 (default) = the occupancy-driven kernel (csrc/aggregate.cu).  Also
+ * GNNA_STAGED=1 in the environment.  Returns the previous setting.  Measured 7-17 % slower than the default on
+ * B200 (the index streams are 1.5 % of the bytes), hence opt-in.                                       */
+GNNA_API int gnna_set_staged(int on);
+
 /* Number of kernels this library has launched on this thread since the last reset
  * (bench.py's "gpu_launches" is read from here, not guessed). */
 GNNA_API int64_t gnna_launch_count(int reset);

@@ -501,3 +501,41 @@ def test_host_aggregator_pipeline():
     for x, o in zip(xs, outs):
         assert_close(o.numpy(), oracle.aggregate(1, x.numpy(), ci, g.deg, 1.0, g.pp, g.pn), what="host pipeline",
                      terms=g.terms(1, x.numpy()))
+
+
+# ------------------------------------------------------------------------------------------ TMA-staged persistent kernel
+@pytest.mark.parametrize("dim", [8, 16, 32, 64, 100, 128])
+@pytest.mark.parametrize("ps", [3, 32, 64])
+def test_staged_tma_kernel(dim, ps):
+    """csrc/aggregate_staged.cu: group table + column indices streamed through cp.async.bulk into a shared-memory
+    ring, persistent CTAs.  Same results as the oracle (bit-identical where a row is one group)."""
+    from gnnadvisor_osdi21_b200 import _lib
+    prev = _lib.set_staged(True)
+    try:
+        for gname in ("rmat", "uniform"):
+            rp, ci = GRAPHS[gname]()
+            g = G(rp, ci, ps)
+            X = rand_features(g.n, dim, 40 + dim)
+            dX = dev(X)
+            assert_close(ops.SAG(dX, *g.gargs(), g.d_deg, *g.pargs(), ps, 32, 4).cpu().numpy(),
+                         oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="staged SAG", terms=g.terms(0, X))
+            assert_close(_gcn_agg(dX, g, 32, 4), oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="staged GCN",
+                         terms=g.terms(1, X))
+            assert_close(_gin_agg(dX, g, 0.5, 32, 4), oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn), what="staged GIN",
+                         terms=g.terms(2, X))
+        # single-group rows stay bit-identical; the F6 table (terminal 0) and isolated nodes go through the direct-load tiles
+        rp, ci = make_graph("uniform", 3000, 20000, 33)
+        g = G(rp, ci, 64)
+        X = rand_features(g.n, dim, 41)
+        assert np.array_equal(_gin_agg(dev(X), g, 0.5, 32, 4), oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn))
+        rng = np.random.default_rng(3)
+        deg = rng.integers(0, 50, 900); deg[::5] = 0; deg[-1] = 0; deg[-2] = 40
+        rp = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        ci = rng.integers(0, 900, rp[-1]).astype(np.int32)
+        X = rand_features(900, dim, 42)
+        for exact in (True, False):
+            g = G(rp, ci, 32, exact=exact)
+            assert_close(ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4).cpu().numpy(),
+                         oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="staged F6 exact=%s" % exact, terms=g.terms(0, X))
+    finally:
+        _lib.set_staged(prev)
