@@ -65,9 +65,11 @@ def peak_gbs():
     return PEAK_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def alg_bytes(E, N, D, P, sx=4, sy=4, gcn=True):
-    """E*(D*sx + 4 [+4 GCN degree gather]) + N*(D*sy + 8) + part table (2P+1)*4."""
-    return E * (D * sx + 4 + (4 if gcn else 0)) + N * (D * sy + 8) + (2 * P + 1) * 4
+def alg_bytes(E, N, D, P, sx=4, sy=4, gcn=False, prescale=False):
+    """E*(D*sx + 4 [+4 per-edge degree gather, exact GCN mode only]) + N*(D*sy + 8) + part table
+    (2P+1)*4 [+ 2*N*D*sx for the pre-scale pass of the default GCN mode]."""
+    return (E * (D * sx + 4 + (4 if gcn else 0)) + N * (D * sy + 8) + (2 * P + 1) * 4
+            + (2 * N * D * sx if prescale else 0))
 
 
 class ClockSampler:
@@ -265,7 +267,7 @@ def run_single(args):
 
     # ---- roofline of the aggregation kernel
     peak, peak_src = peak_gbs()
-    B = alg_bytes(E, N, D, P)
+    B = alg_bytes(E, N, D, P, prescale=True)
     achieved = B / (ms * 1e-3) / 1e9
     traffic, l2_bytes = None, None
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")

@@ -86,6 +86,29 @@ __device__ __forceinline__ void unpack(const Raw<8> &r, float (&f)[4], __nv_bflo
 __device__ __forceinline__ void unpack(const Raw<4> &r, float (&f)[2], __nv_bfloat16) { f[0] = bf16lo(r.v); f[1] = bf16hi(r.v); }
 __device__ __forceinline__ void unpack(const Raw<2> &r, float (&f)[1], __nv_bfloat16) { f[0] = bf16lo(r.v); }
 
+// acc += bf16 elements, fp32 accumulation, with the mixed-precision add of PTX ISA 8.6 (sm_100+):
+// `add.rn.f32.bf16 d, a, c` = fl(float(a) + c) in ONE instruction (SASS FHADD.BF16 with an .H0/.H1 selector),
+// where the conversion is exact -- the same result as unpack + __fadd_rn at half the instruction count.
+__device__ __forceinline__ void add_bf16x2(uint32_t w, float &lo_acc, float &hi_acc) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
+        "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+        : "+f"(lo_acc), "+f"(hi_acc) : "r"(w));
+}
+__device__ __forceinline__ void add_bf16(const Raw<16> &r, float (&a)[8]) {
+    add_bf16x2(r.v.x, a[0], a[1]); add_bf16x2(r.v.y, a[2], a[3]); add_bf16x2(r.v.z, a[4], a[5]); add_bf16x2(r.v.w, a[6], a[7]);
+}
+__device__ __forceinline__ void add_bf16(const Raw<8> &r, float (&a)[4]) {
+    add_bf16x2(r.v.x, a[0], a[1]); add_bf16x2(r.v.y, a[2], a[3]);
+}
+__device__ __forceinline__ void add_bf16(const Raw<4> &r, float (&a)[2]) { add_bf16x2(r.v, a[0], a[1]); }
+__device__ __forceinline__ void add_bf16(const Raw<2> &r, float (&a)[1]) {
+    asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(a[0]) : "h"(r.v));
+}
+// fp32 element types never take this path; the overloads only have to exist for the template to compile
+__device__ __forceinline__ void add_bf16(const Raw<16> &, float (&)[4]) {}
+__device__ __forceinline__ void add_bf16(const Raw<8> &, float (&)[2]) {}
+__device__ __forceinline__ void add_bf16(const Raw<4> &, float (&)[1]) {}
+
 // base + (int64)a * b as ONE IMAD.WIDE (the compiler emits IMAD.WIDE + a 64-bit add otherwise)
 __device__ __forceinline__ const char *mad_wide(int a, int b, const char *base) {
     const char *r;
@@ -120,12 +143,16 @@ __device__ __forceinline__ void batch_step(const char *const (&lane_base)[KCH], 
     for (int u = 0; u < U; u++) {
 #pragma unroll
         for (int k = 0; k < KCH; k++) {
-            float f[VEC];
-            unpack(raw[u][k], f, T());
+            if constexpr (!WEIGHTED && sizeof(T) == 2) {
+                add_bf16(raw[u][k], acc[k]);         // one FHADD.BF16 per element instead of unpack + FADD
+            } else {
+                float f[VEC];
+                unpack(raw[u][k], f, T());
 #pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                if (WEIGHTED) acc[k][v] = __fadd_rn(acc[k][v], __fmul_rn(w[u], f[v]));
-                else acc[k][v] = __fadd_rn(acc[k][v], f[v]);
+                for (int v = 0; v < VEC; v++) {
+                    if (WEIGHTED) acc[k][v] = __fadd_rn(acc[k][v], __fmul_rn(w[u], f[v]));
+                    else acc[k][v] = __fadd_rn(acc[k][v], f[v]);
+                }
             }
         }
     }

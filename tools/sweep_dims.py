@@ -24,7 +24,7 @@ for D in (16, 32, 41, 47, 64, 100, 128, 172, 256, 602):
             continue
         ms = bench.timed(fn, 10, 3) / 10
         row[name + "_ms"] = round(ms, 4)
-        row[name + "_GBs"] = round(bench.alg_bytes(E, N, D, pn.numel(), gcn=False) / ms / 1e6, 0)
+        row[name + "_GBs"] = round(bench.alg_bytes(E, N, D, pn.numel()) / ms / 1e6, 0)
     for wpb in (4, 16):
         ms = bench.timed(lambda: ops.SAG(X, rp, ci, deg, pp, pn, 32, 32, wpb), 10, 3) / 10
         row["SAG_wpb%d_ms" % wpb] = round(ms, 4)
