@@ -45,6 +45,13 @@ SIGNATURES = {
     "gnna_prescale_rows_f32": (i32, [c_f32p, c_f32p, c_f32p, i64, i32, ctypes.c_void_p]),
     "gnna_aggregate_bf16": (i32, [i32, ctypes.c_void_p, c_f32p] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
                             + [i64, i32, i64] + _TUNE),
+    "gnna_scale_rows_bf16": (i32, [c_f32p, ctypes.c_void_p, c_f32p, i64, i32, i32, ctypes.c_void_p]),
+    "gnna_aggregate_bf16_ex": (i32, [i32, ctypes.c_void_p, i32, c_f32p] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
+                               + [i64, i32, i64] + _TUNE),
+    "gnna_forward_mixed": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_f32p] + _GRAPH + [c_f32p] + _PARTS
+                           + [i64, i32, i32, i64] + _TUNE),
+    "gnna_backward_mixed": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p] + _GRAPH + [c_f32p] + _PARTS
+                            + [i64, i32, i32, i64] + _TUNE),
     "gnna_forward_f32": (i32, [c_f32p] * 4 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
     "gnna_backward_f32": (i32, [c_f32p] * 6 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
     "gnna_forward_gin_f32": (i32, [c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p] + _GRAPH + _PARTS

@@ -48,6 +48,16 @@
 #ifndef GNNA_WIDE_MIN_CTAS
 #define GNNA_WIDE_MIN_CTAS 2
 #endif
+// GNNA_CHAIN=1 shortens the dependent-load chain of one neighbour-group (table -> ids -> rows ... -> row_ptr):
+//   * the ids of up to 32 neighbours (a whole group at the default partSize) are fetched in ONE round trip
+//     instead of one round trip per 8 or 16 neighbours;
+//   * the loads the flush needs (row_ptr[src], row_ptr[src+1], degrees[src]) are issued before the gather
+//     instead of after it.
+// Narrow and bf16 rows are latency-bound (neither L2 bytes nor L1 wavefronts saturate), so the chain length is
+// what sets their speed.  GNNA_CHAIN=0 is the previous kernel (kept for A/B runs, tools/ab_chain.py).
+#ifndef GNNA_CHAIN
+#define GNNA_CHAIN 1
+#endif
 
 namespace gnna {
 
@@ -105,7 +115,11 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
 {
     // dim = row stride of `out` (% VEC == 0, 16-byte aligned rows); ldx = row stride of X in elements (>= dim)
     constexpr int S = 32 / LPR;                      // neighbour-groups per warp
-    constexpr int IPL = (LPR >= 8) ? 1 : 8 / LPR;    // neighbour ids fetched per lane per batch
+    // neighbour ids fetched per lane per batch: 32 neighbours per batch (8 at most per lane); the exact-GCN
+    // variant also carries a weight per id and keeps the short batch (it is about rounding, not speed)
+    constexpr int IPL_SHORT = (LPR >= 8) ? 1 : 8 / LPR;
+    constexpr int IPL_LONG = (LPR >= 32) ? 1 : (32 / LPR > 8 ? 8 : 32 / LPR);
+    constexpr int IPL = (GNNA_CHAIN && !WEIGHTED) ? IPL_LONG : IPL_SHORT;
     constexpr int B = LPR * IPL;                     // neighbours per batch (>= 8)
     constexpr int U = (KCH >= 8) ? 1 : 8 / KCH;      // neighbour rows in flight per sub-warp
     static_assert(B % U == 0, "batch must be a multiple of the unroll");
@@ -148,6 +162,50 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
         for (int v = 0; v < VEC; v++) acc[k][v] = 0.f;
     }
 
+#if GNNA_CHAIN
+    // what the flush needs, requested now: the answers arrive while the rows are gathered
+    bool own = false;
+    float mul = (flags & F_SCALE) ? scale : 1.f;
+    {
+        int r0 = 0, r1 = 0;
+        if (len > 0) {
+            r0 = ldg_keep(row_ptr + src);
+            r1 = ldg_keep(row_ptr + src + 1);
+            if (flags & F_ROWSCALE) mul = ldg_keep_f(degrees + src);
+        }
+        // cooperative, coalesced fetch of the first batch's neighbour ids (issued before the compare below waits)
+        int nid[IPL];
+        float wgt[IPL];
+        auto fetch_ids = [&](int base) {
+#pragma unroll
+            for (int i = 0; i < IPL; i++) {
+                const int n = base + i * LPR + l;
+                nid[i] = -1;
+                wgt[i] = 0.f;
+                if (n < len) {
+                    nid[i] = ldg_stream(col_idx + beg + n);
+                    if (WEIGHTED) wgt[i] = __fmul_rn(src_norm, __ldg(degrees + nid[i]));
+                }
+            }
+        };
+        fetch_ids(0);
+        // plain store when this group is the node's whole adjacency list, else vector reduction
+        own = !(flags & F_ACCUMULATE) && (beg == r0) && (end == r1);
+        for (int base = 0; base < maxlen; base += B) {
+            if (base > 0) fetch_ids(base);
+            // steps whose U neighbours every sub-warp of the warp still has need no predicates
+#pragma unroll
+            for (int j0 = 0; j0 < B; j0 += U) {
+                if (base + j0 + U <= minlen) {
+                    batch_step<T, VEC, LPR, KCH, U, IPL, WEIGHTED, false>(lane_base, row_bytes, nchunks, chunk0, j0, nid, wgt, acc);
+                } else {
+                    if (base + j0 >= maxlen) break;
+                    batch_step<T, VEC, LPR, KCH, U, IPL, WEIGHTED, true>(lane_base, row_bytes, nchunks, chunk0, j0, nid, wgt, acc);
+                }
+            }
+        }
+    }
+#else
     for (int base = 0; base < maxlen; base += B) {
         // cooperative, coalesced fetch of this batch's neighbour ids (+ GCN weights in exact mode)
         int nid[IPL];
@@ -176,11 +234,15 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
         }
     }
 
+#endif
+
     if (len > 0) {
+#if !GNNA_CHAIN
         // plain store when this group is the node's whole adjacency list, else vector reduction
         const bool own = !(flags & F_ACCUMULATE) && (beg == __ldg(row_ptr + src)) && (end == __ldg(row_ptr + src + 1));
         float mul = (flags & F_SCALE) ? scale : 1.f;
         if (flags & F_ROWSCALE) mul = __ldg(degrees + src);
+#endif
         float *orow = out + (long long)src * dim;
 #pragma unroll
         for (int k = 0; k < KCH; k++) {
@@ -240,6 +302,41 @@ unpack_rows_kernel(const float *__restrict__ Ys, float *__restrict__ out, long l
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const long long r = i / dim;
         out[i] = Ys[r * ld + (i - r * dim)];
+    }
+}
+
+// Xb[i, 0:dim] = bf16( (degrees ? degrees[i] : 1) * X[i, 0:dim] ), Xb[i, dim:ldb] = 0, ldb % 8 == 0.
+// The producer pass of the mixed-precision layers (gnna_forward_mixed / gnna_backward_mixed): halves the bytes the
+// gather moves and pads odd widths (41, 47 classes) to whole 16-byte chunks in the same pass.  One thread writes
+// one 16-byte chunk (8 bf16); reads are float4 when the row is 16-byte aligned.
+__global__ void __launch_bounds__(256)
+scale_rows_bf16_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ Xb, const float *__restrict__ degrees,
+                       long long num_rows, int dim, int ldb)
+{
+    const int cpr = ldb / 8;
+    const long long total = num_rows * cpr, stride = (long long)gridDim.x * blockDim.x;
+    const bool aligned = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / cpr;
+        const int c0 = (int)(i - r * cpr) * 8;
+        const float n = degrees ? __ldg(degrees + r) : 1.f;
+        const float *xr = X + r * dim;
+        float f[8];
+        if (aligned && c0 + 8 <= dim) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(xr + c0));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(xr + c0 + 4));
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int v = 0; v < 8; v++) f[v] = (c0 + v < dim) ? __ldg(xr + c0 + v) : 0.f;
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(__fmul_rn(n, f[2 * v]), __fmul_rn(n, f[2 * v + 1]));
+            w[v] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        reinterpret_cast<uint4 *>(Xb)[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -385,6 +482,20 @@ int prescale_rows(const float *X, float *Xs, const float *degrees, int64_t num_n
     return repack_rows(X, Xs, degrees, num_nodes, dim, dim, stream);
 }
 
+int scale_rows_bf16(const float *X, void *Xb, const float *degrees, int64_t num_rows, int dim, int ldb, cudaStream_t stream)
+{
+    if (num_rows == 0 || dim == 0) return GNNA_OK;
+    GNNA_REQUIRE(ldb >= dim && ldb % 8 == 0, "scale_rows_bf16: ldb %d must be a multiple of 8 and >= dim %d", ldb, dim);
+    GNNA_REQUIRE(((uintptr_t)Xb & 15) == 0, "scale_rows_bf16: output not 16-byte aligned");
+    const long long items = (long long)num_rows * (ldb / 8);
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    scale_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, reinterpret_cast<__nv_bfloat16 *>(Xb), degrees, num_rows, dim, ldb);
+    GNNA_CUDA_CHECK(cudaGetLastError());
+    count_launch(1);
+    return GNNA_OK;
+}
+
 // stream-ordered scratch: keep freed blocks in the pool instead of returning them to the OS at every sync
 static int scratch_alloc(float **p, size_t bytes, cudaStream_t stream)
 {
@@ -455,6 +566,16 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
                 dim = new_ld;
             }
         }
+    }
+
+    if (elem_bytes == 2 && ldx != dim && num_parts > 0) {
+        // bf16 rows padded to whole 16-byte chunks (scale_rows_bf16): the kernel writes whole chunks, so it
+        // aggregates into an equally padded fp32 scratch that is un-packed at the end
+        GNNA_REQUIRE(ldx % 8 == 0 && !accumulate, "aggregate: padded bf16 rows need ldx %% 8 == 0 and no accumulation");
+        const int rc = scratch_alloc(&out_scratch, sizeof(float) * (size_t)num_nodes * (size_t)ldx, stream);
+        if (rc != GNNA_OK) return rc;
+        out = out_scratch;
+        dim = ldx;
     }
 
     // rows shared by several groups are merged with reductions, rows without neighbours stay zero

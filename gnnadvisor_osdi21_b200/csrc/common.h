@@ -46,4 +46,7 @@ bool gcn_exact_mode();   // GNNA_GCN_EXACT / gnna_set_gcn_exact
 // Xs[i,:] = degrees[i] * X[i,:]  (X == Xs allowed)
 int prescale_rows(const float *X, float *Xs, const float *degrees, int64_t num_nodes, int dim, cudaStream_t stream);
 
+// Xb[i, 0:dim] = bf16(degrees[i] * X[i, :]) (degrees may be NULL: plain conversion), zero-padded to ldb (% 8 == 0) columns
+int scale_rows_bf16(const float *X, void *Xb, const float *degrees, int64_t num_rows, int dim, int ldb, cudaStream_t stream);
+
 }  // namespace gnna

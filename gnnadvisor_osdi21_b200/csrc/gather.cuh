@@ -64,6 +64,19 @@ __device__ __forceinline__ int ldg_stream(const int32_t *p) {
     return v;
 }
 
+// small per-node tables read at the START of a group for its flush (row_ptr, degrees): volatile so they are issued
+// where they are written, not sunk next to their use after the gather
+__device__ __forceinline__ int ldg_keep(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_keep_f(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 

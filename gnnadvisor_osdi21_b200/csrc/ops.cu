@@ -197,6 +197,61 @@ extern "C" int gnna_backward_f32(const float *d_out, const float *X, const float
     return sgemm_rm(st, true, false, din, dout, num_nodes, X, G_ws, d_weight);            // :473
 }
 
+// ---- mixed-precision GCN layer: fp32 dense products, bf16 GATHERED rows, fp32 accumulation and outputs --------
+// (BASELINE.json config "Reddit GCN 2-layer D=64 bf16"; no reference counterpart, the reference is fp32-only)
+static int round_up8(int x) { return (x + 7) / 8 * 8; }
+
+extern "C" int gnna_scale_rows_bf16(const float *X, void *Xb, const float *degrees, int64_t num_rows, int dim, int ldb,
+                                    void *stream)
+{
+    GNNA_REQUIRE(num_rows >= 0 && dim >= 0, "gnna_scale_rows_bf16: negative size");
+    GNNA_REQUIRE(num_rows == 0 || dim == 0 || (X && Xb), "gnna_scale_rows_bf16: null pointer");
+    return scale_rows_bf16(X, Xb, degrees, num_rows, dim, ldb, (cudaStream_t)stream);
+}
+
+extern "C" int gnna_aggregate_bf16_ex(int mode, const void *X_bf16, int ldx, float *out_f32, const int32_t *row_ptr,
+                                      const int32_t *col_idx, const float *degrees, float eps,
+                                      const int32_t *part_ptr, const int32_t *part2node,
+                                      int64_t num_nodes, int dim, int64_t num_parts,
+                                      int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    GNNA_REQUIRE(ldx >= dim, "gnna_aggregate_bf16_ex: ldx %d < dim %d", ldx, dim);
+    return aggregate(mode, 2, X_bf16, out_f32, row_ptr, col_idx, degrees, eps, part_ptr, part2node, num_nodes, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream, ldx);
+}
+
+extern "C" int gnna_forward_mixed(const float *X, const float *W, float *T_ws, void *Tb_ws, float *out,
+                                  const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                                  const int32_t *part_ptr, const int32_t *part2node,
+                                  int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                  int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(X && W && T_ws && Tb_ws && out && degrees, "gnna_forward_mixed: null pointer");
+    const int ld = round_up8(dout);
+    GNNA_TRY(sgemm_rm(st, false, false, num_nodes, dout, din, X, W, T_ws));               // kernel.cu:280
+    GNNA_TRY(scale_rows_bf16(T_ws, Tb_ws, degrees, num_nodes, dout, ld, st));             // Tb_j = bf16(n_j * T_j)
+    return aggregate(MODE_GCN_PRESCALED, 2, Tb_ws, out, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes,
+                     dout, num_parts, part_size, dim_worker, warp_per_block, st, ld);     // out_i = n_i * sum_j Tb_j
+}
+
+extern "C" int gnna_backward_mixed(const float *d_out, const float *X, const float *W, void *Gb_ws, float *G_ws,
+                                   float *d_input, float *d_weight,
+                                   const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                                   const int32_t *part_ptr, const int32_t *part2node,
+                                   int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                   int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(d_out && X && W && Gb_ws && G_ws && d_weight && degrees, "gnna_backward_mixed: null pointer");
+    const int ld = round_up8(dout);
+    GNNA_TRY(scale_rows_bf16(d_out, Gb_ws, degrees, num_nodes, dout, ld, st));
+    GNNA_TRY(aggregate(MODE_GCN_PRESCALED, 2, Gb_ws, G_ws, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes,
+                       dout, num_parts, part_size, dim_worker, warp_per_block, st, ld)); // kernel.cu:436-463
+    if (d_input) GNNA_TRY(sgemm_rm(st, false, true, num_nodes, din, dout, G_ws, W, d_input));   // :472
+    return sgemm_rm(st, true, false, din, dout, num_nodes, X, G_ws, d_weight);            // :473
+}
+
 extern "C" int gnna_forward_gin_f32(const float *X, const float *W, float eps, float *out, float *x_agg,
                                     const int32_t *row_ptr, const int32_t *col_idx,
                                     const int32_t *part_ptr, const int32_t *part2node,

@@ -60,6 +60,28 @@ class GNNAFunction(torch.autograd.Function):
         return d_input, d_weight, None
 
 
+class GNNAFunctionMixed(torch.autograd.Function):
+    """GNNAFunction with the gathered matrix stored as bf16 (extension: BASELINE.json's "Reddit GCN D=64 bf16"
+    configuration; dense products, accumulation, outputs and gradients stay fp32)."""
+
+    @staticmethod
+    def forward(ctx, X, weight, inputInfo):
+        ctx.save_for_backward(X, weight)
+        ctx.inputInfo = inputInfo
+        ctx.tune = _tune(inputInfo)
+        return GNNA.forward_mixed(X, weight, *_graph(inputInfo), inputInfo.degrees,
+                                  inputInfo.partPtr, inputInfo.part2Node, *ctx.tune)[0]
+
+    @staticmethod
+    def backward(ctx, d_output):
+        X, weight = ctx.saved_tensors
+        info = ctx.inputInfo
+        d_input, d_weight = GNNA.backward_mixed(d_output.contiguous(), X, weight, *_graph(info), info.degrees,
+                                                info.partPtr, info.part2Node, *ctx.tune,
+                                                need_d_input=ctx.needs_input_grad[0])
+        return d_input, d_weight, None
+
+
 class GNNAFunction_GIN(torch.autograd.Function):
     """GIN layer: aggregate then update; the aggregated features are what backward needs (gnn_conv.py:101-126)."""
 
@@ -97,7 +119,16 @@ class _ConvBase(torch.nn.Module):
 
 
 class GCNConv(_ConvBase):
+    def __init__(self, input_dim, output_dim, gather_dtype="fp32"):
+        """gather_dtype="bf16" (extension, not in the reference): neighbour rows travel as bf16, see GNNAFunctionMixed."""
+        super().__init__(input_dim, output_dim)
+        if gather_dtype not in ("fp32", "bf16"):
+            raise ValueError("gather_dtype must be 'fp32' or 'bf16'")
+        self.gather_dtype = gather_dtype
+
     def forward(self, X, inputInfo):
+        if self.gather_dtype == "bf16":
+            return GNNAFunctionMixed.apply(X, self.weights, inputInfo)
         return GNNAFunction.apply(X, self.weights, inputInfo)
 
 

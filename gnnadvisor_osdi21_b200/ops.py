@@ -26,6 +26,7 @@ from . import _lib
 
 __all__ = ["SAG", "forward", "backward", "forward_gin", "backward_gin", "build_part",
            "build_part_exact", "aggregate_bf16", "aggregate_gemm_fused", "forward_gin_fused",
+           "forward_mixed", "backward_mixed", "scale_rows_bf16",
            "degrees_from_row_ptr", "launch_info"]
 
 
@@ -175,23 +176,95 @@ def backward_gin(d_output, X, W, row_pointers, column_index, epsilon, part_point
 
 
 def aggregate_bf16(mode, X_bf16, row_pointers, column_index, degrees, epsilon, part_pointers, part2Node,
-                   partSize, dimWorker, warpPerBlock):
+                   partSize, dimWorker, warpPerBlock, dim=None):
     """Extension (no reference counterpart): gather bf16 rows, fp32 accumulate, fp32 out.
     mode: 0 SAG, 1 GCN-normalised (per-edge weights), 2 GIN, 3 GCN on features already scaled by
-    degrees[j] (out_i = degrees[i] * sum_j X[j]; the fast path)."""
+    degrees[j] (out_i = degrees[i] * sum_j X[j]; the fast path).
+    dim: logical width when the rows of X_bf16 are zero-padded to a multiple of 8 columns (scale_rows_bf16);
+    the result is [N, dim]."""
     _check_input(X_bf16, "X", torch.bfloat16)
     _graph_args(row_pointers, column_index, part_pointers, part2Node, X_bf16.device)
     if mode in (1, 3):
         _check_input(degrees, "degrees", torch.float32)
-    n, d = X_bf16.shape
+    n, ld = X_bf16.shape
+    d = ld if dim is None else int(dim)
+    if d > ld or (d != ld and ld % 8 != 0):
+        raise RuntimeError("dim %d does not fit rows of %d columns (padded rows need a multiple of 8)" % (d, ld))
     out = torch.empty((n, d), dtype=torch.float32, device=X_bf16.device)
     with torch.cuda.device(X_bf16.device):
-        _lib.check(_lib.load().gnna_aggregate_bf16(int(mode), _ptr(X_bf16), _ptr(out), _ptr(row_pointers), _ptr(column_index),
-                                                   _ptr(degrees) if mode in (1, 3) else ctypes.c_void_p(0), float(epsilon),
-                                                   _ptr(part_pointers), _ptr(part2Node), n, d, part2Node.numel(),
-                                                   int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+        _lib.check(_lib.load().gnna_aggregate_bf16_ex(int(mode), _ptr(X_bf16), ld, _ptr(out), _ptr(row_pointers), _ptr(column_index),
+                                                      _ptr(degrees) if mode in (1, 3) else ctypes.c_void_p(0), float(epsilon),
+                                                      _ptr(part_pointers), _ptr(part2Node), n, d, part2Node.numel(),
+                                                      int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
                    "aggregate_bf16")
     return out
+
+
+def _pad8(d):
+    return (d + 7) // 8 * 8
+
+
+def scale_rows_bf16(X, degrees=None):
+    """Extension: bf16(degrees[i] * X[i, :]) with rows zero-padded to a multiple of 8 columns (16-byte chunks);
+    degrees=None is a plain conversion.  Returns a [N, round_up(D, 8)] bfloat16 tensor."""
+    _feat2d(X, "X")
+    if degrees is not None:
+        _check_input(degrees, "degrees", torch.float32)
+    n, d = X.shape
+    out = torch.empty((n, _pad8(d)), dtype=torch.bfloat16, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().gnna_scale_rows_bf16(_ptr(X), _ptr(out), _ptr(degrees), n, d, _pad8(d), _stream()),
+                   "scale_rows_bf16")
+    return out
+
+
+def forward_mixed(input, weight, row_pointers, column_index, degrees, part_pointers, part2Node,
+                  partSize, dimWorker, warpPerBlock):
+    """Extension: `forward` with the gathered matrix stored as bf16 (fp32 SGEMM, bf16(n_j * T_j) rows gathered with fp32
+    accumulation, fp32 output).  Same arguments and return as forward()."""
+    _feat2d(input, "input")
+    _feat2d(weight, "weight")
+    _check_input(degrees, "degrees", torch.float32)
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, input.device)
+    n, din = input.shape
+    if weight.shape[0] != din:
+        raise RuntimeError("size mismatch: input [%d, %d] x weight [%d, %d]" % (n, din, weight.shape[0], weight.shape[1]))
+    dout = weight.shape[1]
+    tmp = torch.empty((n, dout), dtype=torch.float32, device=input.device)
+    tmp_b = torch.empty((n, _pad8(dout)), dtype=torch.bfloat16, device=input.device)
+    out = torch.empty((n, dout), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.load().gnna_forward_mixed(_ptr(input), _ptr(weight), _ptr(tmp), _ptr(tmp_b), _ptr(out),
+                                                  _ptr(row_pointers), _ptr(column_index), _ptr(degrees),
+                                                  _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                  int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+                   "forward_mixed")
+    return [out]
+
+
+def backward_mixed(d_output, X, W, row_pointers, column_index, degrees, part_pointers, part2Node,
+                   partSize, dimWorker, warpPerBlock, need_d_input=True):
+    """Extension: `backward` with the gathered matrix (n_j * d_output_j) stored as bf16; products and outputs fp32."""
+    _feat2d(d_output, "d_output")
+    _feat2d(X, "X")
+    _feat2d(W, "W")
+    _check_input(degrees, "degrees", torch.float32)
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, d_output.device)
+    n, dout = d_output.shape
+    din = X.shape[1]
+    if X.shape[0] != n or W.shape[0] != din or W.shape[1] != dout:
+        raise RuntimeError("size mismatch: d_output %s, X %s, W %s" % (tuple(d_output.shape), tuple(X.shape), tuple(W.shape)))
+    g_b = torch.empty((n, _pad8(dout)), dtype=torch.bfloat16, device=X.device)
+    g = torch.empty_like(d_output)
+    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device) if need_d_input else None
+    d_weight = torch.empty((din, dout), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().gnna_backward_mixed(_ptr(d_output), _ptr(X), _ptr(W), _ptr(g_b), _ptr(g), _ptr(d_input),
+                                                   _ptr(d_weight), _ptr(row_pointers), _ptr(column_index), _ptr(degrees),
+                                                   _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                   int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+                   "backward_mixed")
+    return [d_input, d_weight]
 
 
 def aggregate_gemm_fused(mode, X, weight, row_pointers, column_index, degrees, epsilon, part_pointers, part2Node,

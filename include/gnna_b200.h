@@ -169,6 +169,34 @@ GNNA_API int gnna_backward_gin_f32(const float *d_out, const float *x_agg, const
                           int64_t num_nodes, int din, int dout, int64_t num_parts,
                           int part_size, int dim_worker, int warp_per_block, void *stream);
 
+/* ---- mixed-precision GCN layer (BASELINE.json config "Reddit GCN 2-layer D=64 bf16"; the reference is fp32-only) ----
+ * Same operators as gnna_forward_f32 / gnna_backward_f32 (spmm_forward_cuda kernel.cu:267-322, spmm_backward_cuda
+ * :422-476) with the GATHERED matrix stored as bf16: dense products, accumulation and every output stay fp32.
+ *   forward : T = X*W (SGEMM) ; Tb_j = bf16(n_j*T_j) ; out_i = n_i * sum_j Tb_j
+ *   backward: Gb_j = bf16(n_j*dOut_j) ; G_i = n_i * sum_j Gb_j ; dX = G*W^T (d_input may be NULL) ; dW = X^T*G
+ * Tb_ws / Gb_ws: bf16 scratch [N, round_up(dout, 8)] (16-byte aligned); T_ws / G_ws: fp32 scratch [N, dout].  */
+GNNA_API int gnna_forward_mixed(const float *X, const float *W, float *T_ws, void *Tb_ws, float *out,
+                                const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                                const int32_t *part_ptr, const int32_t *part2node,
+                                int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                int part_size, int dim_worker, int warp_per_block, void *stream);
+GNNA_API int gnna_backward_mixed(const float *d_out, const float *X, const float *W, void *Gb_ws, float *G_ws,
+                                 float *d_input, float *d_weight,
+                                 const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,
+                                 const int32_t *part_ptr, const int32_t *part2node,
+                                 int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                 int part_size, int dim_worker, int warp_per_block, void *stream);
+/* Building blocks of the two above.  scale_rows: Xb[i, 0:dim] = bf16(degrees[i] * X[i, :]) (degrees NULL: plain
+ * conversion), columns dim..ldb-1 zero, ldb % 8 == 0.  aggregate_bf16_ex: gnna_aggregate_bf16 on rows of stride ldx
+ * elements (ldx == dim, or ldx % 8 == 0 for padded rows).                                              */
+GNNA_API int gnna_scale_rows_bf16(const float *X, void *Xb_bf16, const float *degrees, int64_t num_rows, int dim, int ldb,
+                                  void *stream);
+GNNA_API int gnna_aggregate_bf16_ex(int mode, const void *X_bf16, int ldx, float *out_f32,
+                                    const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
+                                    const int32_t *part_ptr, const int32_t *part2node,
+                                    int64_t num_nodes, int dim, int64_t num_parts,
+                                    int part_size, int dim_worker, int warp_per_block, void *stream);
+
 /* ---- fused aggregate -> X*W on the tensor cores (csrc/fused_gemm.cu) -----------------------------------
  * out = (c_i * sum_{j in N(i)} X[j,:]) * W in ONE kernel: a CTA gathers 128 destination rows into shared
  * memory, converts them to bf16 and multiplies by W (bf16) with tcgen05.mma, fp32 accumulation in TMEM.

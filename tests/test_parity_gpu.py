@@ -319,6 +319,84 @@ def test_bf16_gather_path(dim):
     assert_close(got, ref, what="bf16 prescaled", terms=g.deg[:, None] * oracle.closed_form(0, np.abs(Xs.float().numpy()), rp, ci))
 
 
+# ------------------------------------------------------------------------------------------ mixed-precision GCN layer
+@pytest.mark.parametrize("dim", [1, 7, 8, 41, 47, 64, 100])
+def test_scale_rows_bf16_is_bit_exact_and_padded(dim):
+    """bf16(fl(n_i * x)) with round-to-nearest-even, rows zero-padded to whole 16-byte chunks: integer/bit work, compared
+    bit for bit with the same two roundings done by torch on the CPU."""
+    n = 333
+    X = torch.from_numpy(rand_features(n, dim, 61))
+    deg = torch.from_numpy(oracle.degrees(make_graph("rmat", n, 4000, 62)[0]))
+    for d in (deg, None):
+        got = ops.scale_rows_bf16(X.to(DEV), None if d is None else d.to(DEV)).cpu()
+        ld = (dim + 7) // 8 * 8
+        assert got.shape == (n, ld) and got.dtype == torch.bfloat16
+        want = (X if d is None else X * d[:, None]).to(torch.bfloat16)
+        assert torch.equal(got[:, :dim].view(torch.int16), want.view(torch.int16))
+        assert (got[:, dim:].view(torch.int16) == 0).all()
+
+
+@pytest.mark.parametrize("dout", [16, 41, 64, 47])
+def test_mixed_precision_gcn_operators(dout):
+    """forward_mixed / backward_mixed (bf16 gathered rows, everything else fp32).
+    (1) the padded-row bf16 gather against the fp32 oracle on the SAME rounded rows: fp32 tolerance (1e-4);
+    (2) the two operators against the fp32 oracle on the unrounded inputs: 1e-2 relative, the bound stated for bf16
+        storage in SURVEY.md 8c (one bf16 rounding per gathered term, 2^-9 relative each)."""
+    n, din = 1500, 40
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+    X, W, dO = rand_features(n, din, 63), rand_weight(din, dout, 64), rand_features(n, dout, 65)
+    a = (*g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4)
+    # (1)
+    Tb = ops.scale_rows_bf16(dev(dO), g.d_deg)
+    got = ops.aggregate_bf16(3, Tb, *g.gargs(), g.d_deg, 0.5, *g.pargs(), 32, 32, 4, dim=dout).cpu().numpy()
+    Tr = Tb[:, :dout].float().cpu().numpy()
+    ref = g.deg[:, None].astype(np.float64) * oracle.closed_form(0, Tr, rp, ci)
+    assert_close(got, ref, what="padded bf16 gather", terms=g.deg[:, None] * oracle.closed_form(0, np.abs(Tr), rp, ci))
+    # (2) bound: |err| <= u * sum|terms| with u = 2^-8, the unit roundoff of bf16 (8 significant bits) -- written as
+    # rtol 1e-2 on max(|ref|, 0.4 * sum|terms|)
+    aX, aW, adO = np.abs(X).astype(np.float64), np.abs(W).astype(np.float64), np.abs(dO).astype(np.float64)
+    y, = ops.forward_mixed(dev(X), dev(W), *a)
+    assert_close(y.cpu().numpy(), oracle.forward(X, W, rp, ci, g.deg, g.pp, g.pn)[0], rtol=1e-2, what="mixed forward",
+                 terms=4 * g.terms(1, aX @ aW))
+    dX, dW = ops.backward_mixed(dev(dO), dev(X), dev(W), *a)
+    odX, odW = oracle.backward(dO, X, W, rp, ci, g.deg, g.pp, g.pn)
+    aG = g.terms(1, adO).astype(np.float64)
+    assert_close(dX.cpu().numpy(), odX, rtol=1e-2, what="mixed dX", terms=4 * (aG @ aW.T))
+    assert_close(dW.cpu().numpy(), odW, rtol=1e-2, what="mixed dW", terms=4 * (aX.T @ aG))
+    dX2, dW2 = ops.backward_mixed(dev(dO), dev(X), dev(W), *a, need_d_input=False)
+    assert dX2 is None
+    assert_close(dW2.cpu().numpy(), dW.cpu().numpy(), what="mixed dW without dX", terms=aX.T @ aG)
+
+
+def test_mixed_precision_gcn_layer_trains():
+    """GCNConv(gather_dtype="bf16") in a 2-layer GCN: loss and weight gradients within 1e-2 of the fp32 layer."""
+    import torch.nn.functional as F
+    n, din, hid, cls = 1500, 32, 64, 41
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+
+    class Info:
+        pass
+    info = Info()
+    info.row_pointers, info.column_index, info.degrees = g.d_rp, g.d_ci, 1.0 / g.d_deg   # keep activations O(1)
+    info.partPtr, info.part2Node = g.d_pp, g.d_pn
+    info.partSize, info.dimWorker, info.warpPerBlock = 32, 32, 4
+    x = dev(rand_features(n, din, 66))
+    y = torch.arange(n, device=DEV) % cls
+    res = {}
+    for kind in ("fp32", "bf16"):
+        torch.manual_seed(7)
+        c1, c2 = layers.GCNConv(din, hid, gather_dtype=kind).to(DEV), layers.GCNConv(hid, cls, gather_dtype=kind).to(DEV)
+        loss = F.nll_loss(F.log_softmax(c2(F.relu(c1(x, info)), info), dim=1), y)
+        loss.backward()
+        res[kind] = (loss.item(), c1.weights.grad.cpu().numpy(), c2.weights.grad.cpu().numpy())
+    assert abs(res["bf16"][0] - res["fp32"][0]) <= 1e-2 * abs(res["fp32"][0])
+    for k in (1, 2):
+        ref = res["fp32"][k]
+        assert np.abs(res["bf16"][k] - ref).max() <= 1e-2 * np.abs(ref).max(), "grad of layer %d" % k
+
+
 # ------------------------------------------------------------------------------------------ autograd layers
 def test_gcn_and_gin_layers_autograd():
     """GCNConv / GINConv modules: forward value and the gradients the reference's backward defines."""

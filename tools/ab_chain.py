@@ -1,0 +1,100 @@
+"""A/B of two builds of libgnna_b200.so on the same device tensors, in ONE process (run on the GPU box).
+
+    python tools/ab_chain.py [--out gpurun_out/ab_chain.json] [--workloads reddit,ogbn-products] [--scale 1.0]
+
+A = the in-tree default library, B = gnnadvisor_osdi21_b200/libgnna_b200_nochain.so (built with
+`python -m gnnadvisor_osdi21_b200.build -DGNNA_CHAIN=0 --out=...`: the kernel before the dependent-load
+chain was shortened).  Both are called through the C ABI (include/gnna_b200.h) with the same pointers;
+results are compared element-wise, then each call is timed with CUDA events (3 warm-ups + 20 calls, A/B
+interleaved twice, best kept)."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from gnnadvisor_osdi21_b200 import _lib, graph, ops  # noqa: E402
+
+
+def bind(path):
+    lib = ctypes.CDLL(path)
+    for name in ("gnna_sag_f32", "gnna_gcn_aggregate_f32", "gnna_gin_aggregate_f32", "gnna_aggregate_bf16"):
+        res, args = _lib.SIGNATURES[name]
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib.gnna_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+def timed(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(reps):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab_chain.json"))
+    ap.add_argument("--workloads", default="reddit,ogbn-products")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--b-lib", default=os.path.join(ROOT, "gnnadvisor_osdi21_b200", "libgnna_b200_nochain.so"))
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    libs = {"A_default": bind(_lib.LIB_PATH), "B_nochain": bind(args.b_lib)}
+    p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+    rows = []
+    for wl in args.workloads.split(","):
+        gr = graph.lookalike(wl, device=dev, scale=args.scale)
+        rp, ci = gr["row_ptr"], gr["col_idx"]
+        pp, pn = ops.build_part(32, rp)
+        deg = ops.degrees_from_row_ptr(rp)
+        N, E, P = gr["num_nodes"], ci.numel(), pn.numel()
+        for D in (16, 32, 48, 64, 128):
+            X = torch.randn(N, D, device=dev)
+            Xb = X.to(torch.bfloat16)
+            outs = {k: torch.empty(N, D, device=dev) for k in libs}
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            cases = {
+                "sag_f32": lambda lib, o: lib.gnna_sag_f32(p(X), p(o), p(rp), p(ci), p(pp), p(pn), N, D, P, 32, 32, 4, st),
+                "gcn_f32": lambda lib, o: lib.gnna_gcn_aggregate_f32(p(X), p(o), p(rp), p(ci), p(deg), p(pp), p(pn), N, D, P, 32, 32, 4, st),
+                "gin_f32_dw_auto": lambda lib, o: lib.gnna_gin_aggregate_f32(p(X), p(o), p(rp), p(ci), 0.5, p(pp), p(pn), N, D, P, 32, 0, 4, st),
+                "sag_bf16": lambda lib, o: lib.gnna_aggregate_bf16(0, p(Xb), p(o), p(rp), p(ci), p(deg), 1.0, p(pp), p(pn), N, D, P, 32, 32, 4, st),
+                "gcn3_bf16": lambda lib, o: lib.gnna_aggregate_bf16(3, p(Xb), p(o), p(rp), p(ci), p(deg), 1.0, p(pp), p(pn), N, D, P, 32, 32, 4, st),
+            }
+            for cname, call in cases.items():
+                row = {"workload": wl, "N": N, "E": E, "D": D, "case": cname}
+                for k, lib in libs.items():
+                    rc = call(lib, outs[k])
+                    if rc != 0:
+                        row[k + "_error"] = (lib.gnna_last_error() or b"?").decode()
+                torch.cuda.synchronize()
+                a, b = outs["A_default"], outs["B_nochain"]
+                row["max_rel_diff"] = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+                best = {k: 1e30 for k in libs}
+                for _ in range(2):
+                    for k, lib in libs.items():
+                        best[k] = min(best[k], timed(lambda: call(lib, outs[k])))
+                for k in libs:
+                    row[k + "_ms"] = round(best[k], 4)
+                row["speedup_A_over_B"] = round(best["B_nochain"] / best["A_default"], 3)
+                rows.append(row)
+                print(row, flush=True)
+            del X, Xb, outs
+        del gr, rp, ci, pp, pn, deg
+        torch.cuda.empty_cache()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump({"A": _lib.LIB_PATH, "B": args.b_lib, "rows": rows}, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
