@@ -344,7 +344,7 @@ def run_single(args):
             # features pre-scaled by n_j and rounded to bf16 inside the timed step (in a fused layer this is the
             # epilogue of the X*W product), then the weight-free bf16 gather with fp32 accumulation (mode 3)
             def f():
-                Xb = (X * deg[:, None]).to(torch.bfloat16)
+                Xb = ops.scale_rows_bf16(X, deg)
                 return ops.aggregate_bf16(3, Xb, rp, ci, deg, 1.0, pp, pn, args.part_size, args.dim_worker, args.warp_per_block)
             bms = timed(f, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
             Bb = alg_bytes(E, N, D, P, sx=2)
@@ -357,6 +357,11 @@ def run_single(args):
             extras["gcn_epoch_ms"] = gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device)
         except Exception as e:   # noqa: BLE001
             extras["gcn_epoch_ms"] = {"error": str(e)}
+        # the same epoch with bf16 gathered rows (BASELINE.json config "Reddit GCN 2-layer D=64 bf16")
+        try:
+            extras["gcn_epoch_ms_bf16_gather"] = gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, gather_dtype="bf16")
+        except Exception as e:   # noqa: BLE001
+            extras["gcn_epoch_ms_bf16_gather"] = {"error": str(e)}
         # the reference's own CUDA kernels, recompiled for sm_100a, on the same tensors
         try:
             extras["ref_gpu"] = ref_gpu(args, X, rp, ci, deg, pp, pn, step, ms)
@@ -370,7 +375,7 @@ def run_single(args):
     print(json.dumps(line))
 
 
-def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device):
+def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, gather_dtype="fp32"):
     import torch.nn.functional as F
     from gnnadvisor_osdi21_b200 import layers
 
@@ -382,7 +387,8 @@ def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device):
     n = gr["num_nodes"]
     x = torch.randn(n, gr["in_dim"], device=device)
     y = torch.ones(n, dtype=torch.long, device=device)
-    c1, c2 = layers.GCNConv(gr["in_dim"], gr["hidden"]).to(device), layers.GCNConv(gr["hidden"], gr["classes"]).to(device)
+    c1 = layers.GCNConv(gr["in_dim"], gr["hidden"], gather_dtype=gather_dtype).to(device)
+    c2 = layers.GCNConv(gr["hidden"], gr["classes"], gather_dtype=gather_dtype).to(device)
     opt = torch.optim.Adam(list(c1.parameters()) + list(c2.parameters()), lr=0.01)
 
     def train():
@@ -393,7 +399,8 @@ def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device):
         opt.step()
     k = max(3, min(args.steps // 5, 20))
     return {"ms": timed(train, k, 3) / k, "epochs_timed": k,
-            "model": "GCN %d-%d-%d, fwd+bwd+Adam (GNNA_main.py:142-202)" % (gr["in_dim"], gr["hidden"], gr["classes"])}
+            "model": "GCN %d-%d-%d, fwd+bwd+Adam (GNNA_main.py:142-202), gathered rows %s"
+                     % (gr["in_dim"], gr["hidden"], gr["classes"], gather_dtype)}
 
 
 def ref_gpu(args, X, rp, ci, deg, pp, pn, our_step, our_ms):

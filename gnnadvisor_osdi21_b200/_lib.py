@@ -52,6 +52,10 @@ SIGNATURES = {
                            + [i64, i32, i32, i64] + _TUNE),
     "gnna_backward_mixed": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p] + _GRAPH + [c_f32p] + _PARTS
                             + [i64, i32, i32, i64] + _TUNE),
+    "gnna_forward_gin_mixed": (i32, [c_f32p, c_f32p, ctypes.c_float, ctypes.c_void_p, c_f32p, c_f32p] + _GRAPH + _PARTS
+                               + [i64, i32, i32, i64] + _TUNE),
+    "gnna_backward_gin_mixed": (i32, [c_f32p, c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.c_void_p, c_f32p, c_f32p]
+                                + _GRAPH + _PARTS + [i64, i32, i32, i64] + _TUNE),
     "gnna_forward_f32": (i32, [c_f32p] * 4 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
     "gnna_backward_f32": (i32, [c_f32p] * 6 + _GRAPH + [c_f32p] + _PARTS + [i64, i32, i32, i64] + _TUNE),
     "gnna_forward_gin_f32": (i32, [c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p] + _GRAPH + _PARTS

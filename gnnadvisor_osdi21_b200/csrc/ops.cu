@@ -252,6 +252,40 @@ extern "C" int gnna_backward_mixed(const float *d_out, const float *X, const flo
     return sgemm_rm(st, true, false, din, dout, num_nodes, X, G_ws, d_weight);            // :473
 }
 
+// mixed-precision GIN layer: the gathered matrices (X forward, Pm = dOut*W^T backward) travel as bf16
+extern "C" int gnna_forward_gin_mixed(const float *X, const float *W, float eps, void *Xb_ws, float *out, float *x_agg,
+                                      const int32_t *row_ptr, const int32_t *col_idx,
+                                      const int32_t *part_ptr, const int32_t *part2node,
+                                      int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                      int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(X && W && Xb_ws && out && x_agg, "gnna_forward_gin_mixed: null pointer");
+    const int ld = round_up8(din);
+    GNNA_TRY(scale_rows_bf16(X, Xb_ws, nullptr, num_nodes, din, ld, st));
+    GNNA_TRY(aggregate(MODE_GIN, 2, Xb_ws, x_agg, row_ptr, col_idx, nullptr, eps, part_ptr, part2node, num_nodes, din,
+                       num_parts, part_size, dim_worker, warp_per_block, st, ld));        // kernel.cu:572-603
+    return sgemm_rm(st, false, false, num_nodes, dout, din, x_agg, W, out);               // :605
+}
+
+extern "C" int gnna_backward_gin_mixed(const float *d_out, const float *x_agg, const float *W, float eps,
+                                       float *Pm_ws, void *Pmb_ws, float *d_input, float *d_weight,
+                                       const int32_t *row_ptr, const int32_t *col_idx,
+                                       const int32_t *part_ptr, const int32_t *part2node,
+                                       int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                       int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNA_REQUIRE(d_out && x_agg && W && d_weight && (!d_input || (Pm_ws && Pmb_ws)), "gnna_backward_gin_mixed: null pointer");
+    GNNA_TRY(sgemm_rm(st, true, false, din, dout, num_nodes, x_agg, d_out, d_weight));    // kernel.cu:710
+    if (!d_input) return GNNA_OK;
+    const int ld = round_up8(din);
+    GNNA_TRY(sgemm_rm(st, false, true, num_nodes, din, dout, d_out, W, Pm_ws));           // :711
+    GNNA_TRY(scale_rows_bf16(Pm_ws, Pmb_ws, nullptr, num_nodes, din, ld, st));
+    return aggregate(MODE_GIN, 2, Pmb_ws, d_input, row_ptr, col_idx, nullptr, eps, part_ptr, part2node, num_nodes, din,
+                     num_parts, part_size, dim_worker, warp_per_block, st, ld);           // :712-738
+}
+
 extern "C" int gnna_forward_gin_f32(const float *X, const float *W, float eps, float *out, float *x_agg,
                                     const int32_t *row_ptr, const int32_t *col_idx,
                                     const int32_t *part_ptr, const int32_t *part2node,

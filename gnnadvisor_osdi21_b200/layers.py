@@ -105,9 +105,36 @@ class GNNAFunction_GIN(torch.autograd.Function):
         return d_input, d_weight, None, None
 
 
+class GNNAFunction_GIN_Mixed(torch.autograd.Function):
+    """GNNAFunction_GIN with bf16 gathered rows (extension; accumulation, saved X_agg, products and gradients fp32)."""
+
+    @staticmethod
+    def forward(ctx, X, weight, inputInfo, eplison):
+        X_prime, X_agg = GNNA.forward_gin_mixed(X, weight, *_graph(inputInfo), eplison,
+                                                inputInfo.partPtr, inputInfo.part2Node, *_tune(inputInfo))
+        ctx.save_for_backward(X_agg, weight)
+        ctx.inputInfo = inputInfo
+        ctx.tune = _tune(inputInfo)
+        ctx.eplison = eplison
+        return X_prime
+
+    @staticmethod
+    def backward(ctx, d_output):
+        X_agg, weight = ctx.saved_tensors
+        info = ctx.inputInfo
+        d_input, d_weight = GNNA.backward_gin_mixed(d_output.contiguous(), X_agg, weight, *_graph(info), ctx.eplison,
+                                                    info.partPtr, info.part2Node, *ctx.tune,
+                                                    need_d_input=ctx.needs_input_grad[0])
+        return d_input, d_weight, None, None
+
+
 class _ConvBase(torch.nn.Module):
-    def __init__(self, input_dim, output_dim):
+    def __init__(self, input_dim, output_dim, gather_dtype="fp32"):
+        """gather_dtype="bf16" (extension, not in the reference): neighbour rows travel as bf16, everything else fp32."""
         super().__init__()
+        if gather_dtype not in ("fp32", "bf16"):
+            raise ValueError("gather_dtype must be 'fp32' or 'bf16'")
+        self.gather_dtype = gather_dtype
         self.weights = torch.nn.Parameter(torch.empty(input_dim, output_dim))
         self.reset_parameters()
 
@@ -119,23 +146,16 @@ class _ConvBase(torch.nn.Module):
 
 
 class GCNConv(_ConvBase):
-    def __init__(self, input_dim, output_dim, gather_dtype="fp32"):
-        """gather_dtype="bf16" (extension, not in the reference): neighbour rows travel as bf16, see GNNAFunctionMixed."""
-        super().__init__(input_dim, output_dim)
-        if gather_dtype not in ("fp32", "bf16"):
-            raise ValueError("gather_dtype must be 'fp32' or 'bf16'")
-        self.gather_dtype = gather_dtype
-
     def forward(self, X, inputInfo):
-        if self.gather_dtype == "bf16":
-            return GNNAFunctionMixed.apply(X, self.weights, inputInfo)
-        return GNNAFunction.apply(X, self.weights, inputInfo)
+        fn = GNNAFunctionMixed if self.gather_dtype == "bf16" else GNNAFunction
+        return fn.apply(X, self.weights, inputInfo)
 
 
 class GINConv(_ConvBase):
-    def __init__(self, input_dim, output_dim):
-        super().__init__(input_dim, output_dim)
+    def __init__(self, input_dim, output_dim, gather_dtype="fp32"):
+        super().__init__(input_dim, output_dim, gather_dtype)
         self.eplison = 0.5          # fixed in the reference (gnn_conv.py:132); spelling kept
 
     def forward(self, X, inputInfo):
-        return GNNAFunction_GIN.apply(X, self.weights, inputInfo, self.eplison)
+        fn = GNNAFunction_GIN_Mixed if self.gather_dtype == "bf16" else GNNAFunction_GIN
+        return fn.apply(X, self.weights, inputInfo, self.eplison)

@@ -46,7 +46,7 @@ def build_parser():
     p.add_argument("--synthetic", type=str, default="", help="look-alike graph name[:scale] instead of a dataset file")
     p.add_argument("--decider", type=str, default="reference", choices=["reference", "b200"], help="auto-mode parameter choice")
     p.add_argument("--gather_dtype", type=str, default="fp32", choices=["fp32", "bf16"],
-                   help="GCN only (extension): neighbour rows gathered as bf16, everything else fp32")
+                   help="extension: neighbour rows gathered as bf16, everything else fp32")
     return p
 
 
@@ -137,8 +137,7 @@ def main(argv=None):
     conv = layers.GCNConv if args.model == "gcn" else layers.GINConv
     dims = ([dataset.num_features, args.hidden, dataset.num_classes] if args.model == "gcn"
             else [dataset.num_features] + [args.hidden] * 4 + [dataset.num_classes])     # GNNA_main.py:142-171
-    extra = {"gather_dtype": args.gather_dtype} if args.model == "gcn" else {}
-    convs = torch.nn.ModuleList([conv(a, b, **extra) for a, b in zip(dims[:-1], dims[1:])]).to(device)
+    convs = torch.nn.ModuleList([conv(a, b, gather_dtype=args.gather_dtype) for a, b in zip(dims[:-1], dims[1:])]).to(device)
     if verbose:
         print(convs)
     optimizer = torch.optim.Adam(convs.parameters(), lr=0.01)

@@ -26,7 +26,7 @@ from . import _lib
 
 __all__ = ["SAG", "forward", "backward", "forward_gin", "backward_gin", "build_part",
            "build_part_exact", "aggregate_bf16", "aggregate_gemm_fused", "forward_gin_fused",
-           "forward_mixed", "backward_mixed", "scale_rows_bf16",
+           "forward_mixed", "backward_mixed", "forward_gin_mixed", "backward_gin_mixed", "scale_rows_bf16",
            "degrees_from_row_ptr", "launch_info"]
 
 
@@ -264,6 +264,53 @@ def backward_mixed(d_output, X, W, row_pointers, column_index, degrees, part_poi
                                                    _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
                                                    int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
                    "backward_mixed")
+    return [d_input, d_weight]
+
+
+def forward_gin_mixed(input, weight, row_pointers, column_index, epsilon, part_pointers, part2Node,
+                      partSize, dimWorker, warpPerBlock):
+    """Extension: `forward_gin` with the gathered rows stored as bf16 (fp32 accumulation, X_agg and out fp32)."""
+    _feat2d(input, "input")
+    _feat2d(weight, "weight")
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, input.device)
+    n, din = input.shape
+    if weight.shape[0] != din:
+        raise RuntimeError("size mismatch: input [%d, %d] x weight [%d, %d]" % (n, din, weight.shape[0], weight.shape[1]))
+    dout = weight.shape[1]
+    xb = torch.empty((n, _pad8(din)), dtype=torch.bfloat16, device=input.device)
+    x_agg = torch.empty_like(input)
+    out = torch.empty((n, dout), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.load().gnna_forward_gin_mixed(_ptr(input), _ptr(weight), float(epsilon), _ptr(xb), _ptr(out), _ptr(x_agg),
+                                                      _ptr(row_pointers), _ptr(column_index),
+                                                      _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                      int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+                   "forward_gin_mixed")
+    return [out, x_agg]
+
+
+def backward_gin_mixed(d_output, X, W, row_pointers, column_index, epsilon, part_pointers, part2Node,
+                       partSize, dimWorker, warpPerBlock, need_d_input=True):
+    """Extension: `backward_gin` with Pm = d_output @ W^T gathered as bf16 (X is the saved X_agg)."""
+    _feat2d(d_output, "d_output")
+    _feat2d(X, "X")
+    _feat2d(W, "W")
+    _graph_args(row_pointers, column_index, part_pointers, part2Node, d_output.device)
+    n, dout = d_output.shape
+    din = X.shape[1]
+    if X.shape[0] != n or W.shape[0] != din or W.shape[1] != dout:
+        raise RuntimeError("size mismatch: d_output %s, X %s, W %s" % (tuple(d_output.shape), tuple(X.shape), tuple(W.shape)))
+    pm = torch.empty((n, din), dtype=torch.float32, device=X.device) if need_d_input else None
+    pmb = torch.empty((n, _pad8(din)), dtype=torch.bfloat16, device=X.device) if need_d_input else None
+    d_input = torch.empty((n, din), dtype=torch.float32, device=X.device) if need_d_input else None
+    d_weight = torch.empty((din, dout), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().gnna_backward_gin_mixed(_ptr(d_output), _ptr(X), _ptr(W), float(epsilon), _ptr(pm), _ptr(pmb),
+                                                       _ptr(d_input), _ptr(d_weight),
+                                                       _ptr(row_pointers), _ptr(column_index),
+                                                       _ptr(part_pointers), _ptr(part2Node), n, din, dout, part2Node.numel(),
+                                                       int(partSize), int(dimWorker), int(warpPerBlock), _stream()),
+                   "backward_gin_mixed")
     return [d_input, d_weight]
 
 

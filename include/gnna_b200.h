@@ -169,7 +169,7 @@ GNNA_API int gnna_backward_gin_f32(const float *d_out, const float *x_agg, const
                           int64_t num_nodes, int din, int dout, int64_t num_parts,
                           int part_size, int dim_worker, int warp_per_block, void *stream);
 
-/* ---- mixed-precision GCN layer (BASELINE.json config "Reddit GCN 2-layer D=64 bf16"; the reference is fp32-only) ----
+/* ---- mixed-precision layers (BASELINE.json config "Reddit GCN 2-layer D=64 bf16"; the reference is fp32-only) ----
  * Same operators as gnna_forward_f32 / gnna_backward_f32 (spmm_forward_cuda kernel.cu:267-322, spmm_backward_cuda
  * :422-476) with the GATHERED matrix stored as bf16: dense products, accumulation and every output stay fp32.
  *   forward : T = X*W (SGEMM) ; Tb_j = bf16(n_j*T_j) ; out_i = n_i * sum_j Tb_j
@@ -186,7 +186,21 @@ GNNA_API int gnna_backward_mixed(const float *d_out, const float *X, const float
                                  const int32_t *part_ptr, const int32_t *part2node,
                                  int64_t num_nodes, int din, int dout, int64_t num_parts,
                                  int part_size, int dim_worker, int warp_per_block, void *stream);
-/* Building blocks of the two above.  scale_rows: Xb[i, 0:dim] = bf16(degrees[i] * X[i, :]) (degrees NULL: plain
+/* The GIN pair the same way (spmm_forward_cuda_gin kernel.cu:559-617, spmm_backward_cuda_gin :696-747): the gathered
+ * matrices (X forward; Pm = dOut*W^T backward) are converted to bf16 first.  Xb_ws / Pmb_ws: bf16 scratch
+ * [N, round_up(din, 8)]; x_agg, Pm_ws, d_input (may be NULL: only dW), d_weight as in the fp32 pair.             */
+GNNA_API int gnna_forward_gin_mixed(const float *X, const float *W, float eps, void *Xb_ws, float *out, float *x_agg,
+                                    const int32_t *row_ptr, const int32_t *col_idx,
+                                    const int32_t *part_ptr, const int32_t *part2node,
+                                    int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                    int part_size, int dim_worker, int warp_per_block, void *stream);
+GNNA_API int gnna_backward_gin_mixed(const float *d_out, const float *x_agg, const float *W, float eps,
+                                     float *Pm_ws, void *Pmb_ws, float *d_input, float *d_weight,
+                                     const int32_t *row_ptr, const int32_t *col_idx,
+                                     const int32_t *part_ptr, const int32_t *part2node,
+                                     int64_t num_nodes, int din, int dout, int64_t num_parts,
+                                     int part_size, int dim_worker, int warp_per_block, void *stream);
+/* Building blocks of the four above.  scale_rows: Xb[i, 0:dim] = bf16(degrees[i] * X[i, :]) (degrees NULL: plain
  * conversion), columns dim..ldb-1 zero, ldb % 8 == 0.  aggregate_bf16_ex: gnna_aggregate_bf16 on rows of stride ldx
  * elements (ldx == dim, or ldx % 8 == 0 for padded rows).                                              */
 GNNA_API int gnna_scale_rows_bf16(const float *X, void *Xb_bf16, const float *degrees, int64_t num_rows, int dim, int ldb,

@@ -369,8 +369,34 @@ def test_mixed_precision_gcn_operators(dout):
     assert_close(dW2.cpu().numpy(), dW.cpu().numpy(), what="mixed dW without dX", terms=aX.T @ aG)
 
 
-def test_mixed_precision_gcn_layer_trains():
-    """GCNConv(gather_dtype="bf16") in a 2-layer GCN: loss and weight gradients within 1e-2 of the fp32 layer."""
+@pytest.mark.parametrize("din,dout", [(100, 64), (64, 47), (24, 16)])
+def test_mixed_precision_gin_operators(din, dout):
+    """forward_gin_mixed / backward_gin_mixed against the fp32 oracle, bound u_bf16 * sum|terms| (see above); the saved
+    X_agg against the oracle on the bf16-rounded X at the fp32 tolerance."""
+    n = 1500
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+    X, W, dO = rand_features(n, din, 67), rand_weight(din, dout, 68), rand_features(n, dout, 69)
+    a = (*g.gargs(), 0.5, *g.pargs(), 32, 32, 4)
+    aX, aW, adO = np.abs(X).astype(np.float64), np.abs(W).astype(np.float64), np.abs(dO).astype(np.float64)
+    y, S = ops.forward_gin_mixed(dev(X), dev(W), *a)
+    Xr = torch.from_numpy(X).to(torch.bfloat16).float().numpy()
+    assert_close(S.cpu().numpy(), oracle.aggregate(2, Xr, ci, g.deg, 0.5, g.pp, g.pn), what="mixed gin X_agg", terms=g.terms(2, Xr))
+    oy, oS = oracle.forward_gin(X, W, rp, ci, 0.5, g.pp, g.pn)
+    assert_close(y.cpu().numpy(), oy, rtol=1e-2, what="mixed gin out", terms=4 * (g.terms(2, aX).astype(np.float64) @ aW))
+    dX, dW = ops.backward_gin_mixed(dev(dO), S, dev(W), *a)
+    Sn = S.cpu().numpy()
+    odX, odW = oracle.backward_gin(dO, Sn, W, rp, ci, 0.5, g.pp, g.pn)
+    assert_close(dX.cpu().numpy(), odX, rtol=1e-2, what="mixed gin dX", terms=4 * g.terms(2, adO @ aW.T))
+    assert_close(dW.cpu().numpy(), odW, what="mixed gin dW", terms=np.abs(Sn.T).astype(np.float64) @ adO)
+    dX2, dW2 = ops.backward_gin_mixed(dev(dO), S, dev(W), *a, need_d_input=False)
+    assert dX2 is None
+    assert_close(dW2.cpu().numpy(), odW, what="mixed gin dW only", terms=np.abs(Sn.T).astype(np.float64) @ adO)
+
+
+@pytest.mark.parametrize("model", ["gcn", "gin"])
+def test_mixed_precision_layers_train(model):
+    """GCNConv / GINConv(gather_dtype="bf16") in a 2-layer model: loss and weight gradients within 1e-2 of the fp32 layers."""
     import torch.nn.functional as F
     n, din, hid, cls = 1500, 32, 64, 41
     rp, ci = GRAPHS["rmat"]()
@@ -387,7 +413,10 @@ def test_mixed_precision_gcn_layer_trains():
     res = {}
     for kind in ("fp32", "bf16"):
         torch.manual_seed(7)
-        c1, c2 = layers.GCNConv(din, hid, gather_dtype=kind).to(DEV), layers.GCNConv(hid, cls, gather_dtype=kind).to(DEV)
+        conv = layers.GCNConv if model == "gcn" else layers.GINConv
+        c1, c2 = conv(din, hid, gather_dtype=kind).to(DEV), conv(hid, cls, gather_dtype=kind).to(DEV)
+        if model == "gin":
+            c1.eplison = c2.eplison = 0.02           # keep activations O(1) (no degree normalisation in GIN)
         loss = F.nll_loss(F.log_softmax(c2(F.relu(c1(x, info)), info), dim=1), y)
         loss.backward()
         res[kind] = (loss.item(), c1.weights.grad.cpu().numpy(), c2.weights.grad.cpu().numpy())
