@@ -24,6 +24,10 @@
 #include "common.h"
 #include "gather.cuh"
 
+#ifndef GNNA_CHAIN
+#define GNNA_CHAIN 1   // 1: software-pipelined gather (table + ids of the next group prefetched); 0: the first version
+#endif
+
 namespace gnna {
 
 constexpr int TILE_M = 128;
@@ -67,7 +71,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 template <typename T, int DIN>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
 fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W, float *__restrict__ out,
-                            float *__restrict__ x_agg, const int32_t *__restrict__ col_idx,
+                            float *__restrict__ x_agg, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                             const float *__restrict__ degrees, const int32_t *__restrict__ part_ptr,
                             const int32_t *__restrict__ part2node, long long num_nodes, long long num_parts,
                             int dout, int npad, float scale, int flags)
@@ -77,7 +81,11 @@ fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W
     static_assert(LPR >= 4 && LPR <= 32, "DIN/VEC must be a sub-warp width");
     constexpr int NSUB = FUSED_THREADS / LPR;           // sub-warps per CTA
     constexpr int U = 8;
+#if GNNA_CHAIN
+    constexpr int B = 32;                               // ids of a whole group (default partSize) in one round trip
+#else
     constexpr int B = (LPR >= 8) ? LPR : 8;
+#endif
     constexpr int IPL = B / LPR;
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -104,6 +112,7 @@ fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W
         };
         s_range[0] = lower(row0);
         s_range[1] = lower(row0 + TILE_M);
+        s_range[2] = (long long)__ldg(row_ptr + num_nodes);   // entries of col_idx: bound of the speculative id prefetch
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -147,6 +156,71 @@ fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W
                 }
             }
         };
+#if GNNA_CHAIN
+        // Software pipeline over the run: the table entries AND the neighbour ids of group i+1 are requested before the
+        // rows of group i are gathered, so the dependent chain of a group is its row loads only.  Groups of a run are
+        // contiguous in col_idx (part_ptr[g+1] ends group g and begins group g+1), so the ids of the next group start
+        // at `end`; they are fetched speculatively (bounded by the length of col_idx) and masked by the group's length
+        // once the table entry arrived.
+        const int e_limit = (int)s_range[2];
+        int src_n = -1, beg_n = 0, end_n = 0;
+        int nid_n[IPL];
+        auto prefetch_ids = [&](int from) {
+#pragma unroll
+            for (int q = 0; q < IPL; q++) {
+                const int k = from + q * LPR + l;
+                nid_n[q] = (k < e_limit) ? ldg_stream(col_idx + k) : -1;
+            }
+        };
+#pragma unroll
+        for (int q = 0; q < IPL; q++) nid_n[q] = -1;
+        if (my_begin < my_end) {
+            src_n = ldg_stream(part2node + my_begin);
+            beg_n = ldg_stream(part_ptr + my_begin);
+            end_n = ldg_stream(part_ptr + my_begin + 1);
+            prefetch_ids(beg_n);
+        }
+        for (long long i = 0; i < chunk; i++) {            // warp-uniform trip count
+            const long long g = my_begin + i;
+            const bool gvalid = g < my_end;
+            const int src = gvalid ? src_n : -1, beg = beg_n, end = end_n;
+            const int len = gvalid ? max(end - beg, 0) : 0;
+            int nid[IPL];
+            float wgt[IPL];
+#pragma unroll
+            for (int q = 0; q < IPL; q++) {
+                nid[q] = (q * LPR + l < len) ? nid_n[q] : -1;
+                wgt[q] = 0.f;
+            }
+            if (g + 1 < my_end) {                          // request group i+1
+                src_n = ldg_stream(part2node + g + 1);
+                beg_n = end;
+                end_n = ldg_stream(part_ptr + g + 2);
+                prefetch_ids(end);
+            }
+            if (gvalid && src != cur) { flush(); cur = src; }
+            const int maxlen = __reduce_max_sync(FULL, len);
+            const int minlen = __reduce_min_sync(FULL, len);
+            for (int base = 0; base < maxlen; base += B) {
+                if (base > 0) {                            // groups longer than one batch (partSize > 32): direct loads
+#pragma unroll
+                    for (int q = 0; q < IPL; q++) {
+                        const int n = base + q * LPR + l;
+                        nid[q] = (n < len) ? ldg_stream(col_idx + beg + n) : -1;
+                    }
+                }
+#pragma unroll
+                for (int j0 = 0; j0 < B; j0 += U) {
+                    if (base + j0 + U <= minlen) {
+                        batch_step<T, VEC, LPR, 1, U, IPL, false, false>(lane_base, row_bytes, LPR, l, j0, nid, wgt, acc);
+                    } else {
+                        if (base + j0 >= maxlen) break;
+                        batch_step<T, VEC, LPR, 1, U, IPL, false, true>(lane_base, row_bytes, LPR, l, j0, nid, wgt, acc);
+                    }
+                }
+            }
+        }
+#else
         for (long long i = 0; i < chunk; i++) {            // warp-uniform trip count
             const long long g = my_begin + i;
             const bool gvalid = g < my_end;
@@ -183,6 +257,7 @@ fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W
                 }
             }
         }
+#endif
         flush();
     }
     __syncthreads();
@@ -268,7 +343,8 @@ fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W
 static int fused_smem_bytes(int din, int npad) { return TILE_M * din * 4 + TILE_M * din * 2 + npad * din * 2 + 64; }
 
 template <typename T, int DIN>
-static int launch_fused(const void *X, const float *W, float *out, float *x_agg, const int32_t *col_idx, const float *degrees,
+static int launch_fused(const void *X, const float *W, float *out, float *x_agg, const int32_t *row_ptr,
+                        const int32_t *col_idx, const float *degrees,
                         const int32_t *part_ptr, const int32_t *part2node, int64_t num_nodes, int64_t num_parts, int dout,
                         int npad, float scale, int flags, cudaStream_t stream)
 {
@@ -278,7 +354,7 @@ static int launch_fused(const void *X, const float *W, float *out, float *x_agg,
     auto kern = fused_aggregate_gemm_kernel<T, DIN>;
     GNNA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long tiles = (num_nodes + TILE_M - 1) / TILE_M;
-    kern<<<(unsigned)tiles, FUSED_THREADS, smem, stream>>>(reinterpret_cast<const T *>(X), W, out, x_agg, col_idx, degrees,
+    kern<<<(unsigned)tiles, FUSED_THREADS, smem, stream>>>(reinterpret_cast<const T *>(X), W, out, x_agg, row_ptr, col_idx, degrees,
                                                           part_ptr, part2node, (long long)num_nodes, (long long)num_parts,
                                                           dout, npad, scale, flags);
     GNNA_CUDA_CHECK(cudaGetLastError());
@@ -297,13 +373,13 @@ extern "C" int gnna_aggregate_gemm_fused_bf16(int mode, const void *X, int x_is_
                                               int64_t num_nodes, int din, int dout, int64_t num_parts,
                                               int part_size, int dim_worker, int warp_per_block, void *stream_)
 {
-    (void)row_ptr; (void)part_size; (void)dim_worker; (void)warp_per_block;
+    (void)part_size; (void)dim_worker; (void)warp_per_block;
     cudaStream_t stream = (cudaStream_t)stream_;
     GNNA_REQUIRE(mode == MODE_SAG || mode == MODE_GIN || mode == MODE_GCN_PRESCALED,
                  "aggregate_gemm_fused: mode %d not supported (0 SAG, 2 GIN, 3 GCN on pre-scaled features)", mode);
     GNNA_REQUIRE(num_nodes >= 0 && num_parts >= 0, "aggregate_gemm_fused: negative size");
     if (num_nodes == 0) return GNNA_OK;
-    GNNA_REQUIRE(X && W && out && (num_parts == 0 || (col_idx && part_ptr && part2node)), "aggregate_gemm_fused: null pointer");
+    GNNA_REQUIRE(X && W && out && row_ptr && (num_parts == 0 || (col_idx && part_ptr && part2node)), "aggregate_gemm_fused: null pointer");
     GNNA_REQUIRE(mode != MODE_GCN_PRESCALED || degrees, "aggregate_gemm_fused: GCN mode needs degrees");
     GNNA_REQUIRE(dout >= 1 && dout <= 256, "aggregate_gemm_fused: dout %d out of range (1..256)", dout);
     int npad = 16;
@@ -311,7 +387,7 @@ extern "C" int gnna_aggregate_gemm_fused_bf16(int mode, const void *X, int x_is_
     const float scale = (mode == MODE_GIN) ? eps : 1.f;
     const int flags = (mode == MODE_GIN ? 1 : 0) | (mode == MODE_GCN_PRESCALED ? 2 : 0);
 #define GNNA_FUSED_CASE(TYPE, DIN)                                                                               \
-    return launch_fused<TYPE, DIN>(X, W, out, x_agg, col_idx, degrees, part_ptr, part2node, num_nodes, num_parts, \
+    return launch_fused<TYPE, DIN>(X, W, out, x_agg, row_ptr, col_idx, degrees, part_ptr, part2node, num_nodes, num_parts, \
                                    dout, npad, scale, flags, stream)
     if (!x_is_bf16) {
         if (din == 64) GNNA_FUSED_CASE(float, 64);

@@ -21,7 +21,8 @@ from gnnadvisor_osdi21_b200 import _lib, graph, ops  # noqa: E402
 
 def bind(path):
     lib = ctypes.CDLL(path)
-    for name in ("gnna_sag_f32", "gnna_gcn_aggregate_f32", "gnna_gin_aggregate_f32", "gnna_aggregate_bf16"):
+    for name in ("gnna_sag_f32", "gnna_gcn_aggregate_f32", "gnna_gin_aggregate_f32", "gnna_aggregate_bf16",
+                 "gnna_aggregate_gemm_fused_bf16"):
         res, args = _lib.SIGNATURES[name]
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
@@ -71,6 +72,16 @@ def main():
                 "sag_bf16": lambda lib, o: lib.gnna_aggregate_bf16(0, p(Xb), p(o), p(rp), p(ci), p(deg), 1.0, p(pp), p(pn), N, D, P, 32, 32, 4, st),
                 "gcn3_bf16": lambda lib, o: lib.gnna_aggregate_bf16(3, p(Xb), p(o), p(rp), p(ci), p(deg), 1.0, p(pp), p(pn), N, D, P, 32, 32, 4, st),
             }
+            if D in (64, 128):   # fused aggregate -> X*W tile (tcgen05), GIN form, dout = D; x_agg written
+                Wf = (torch.rand(D, D, device=dev) * 2 - 1) / D ** 0.5
+                xaggs = {k: torch.empty(N, D, device=dev) for k in libs}
+                nul = ctypes.c_void_p(0)
+                cases["fused_gin_f32x"] = lambda lib, o: lib.gnna_aggregate_gemm_fused_bf16(
+                    2, p(X), 0, p(Wf), 0.5, p(o), nul, p(rp), p(ci), nul, p(pp), p(pn), N, D, D, P, 32, 32, 4, st)
+                cases["fused_gin_bf16x"] = lambda lib, o: lib.gnna_aggregate_gemm_fused_bf16(
+                    2, p(Xb), 1, p(Wf), 0.5, p(o), nul, p(rp), p(ci), nul, p(pp), p(pn), N, D, D, P, 32, 32, 4, st)
+                cases["fused_gin_bf16x_xagg"] = lambda lib, o: lib.gnna_aggregate_gemm_fused_bf16(
+                    2, p(Xb), 1, p(Wf), 0.5, p(o), p(xaggs["A_default"]), p(rp), p(ci), nul, p(pp), p(pn), N, D, D, P, 32, 32, 4, st)
             for cname, call in cases.items():
                 row = {"workload": wl, "N": N, "E": E, "D": D, "case": cname}
                 for k, lib in libs.items():
