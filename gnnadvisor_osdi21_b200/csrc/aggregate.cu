@@ -58,6 +58,12 @@
 #ifndef GNNA_CHAIN
 #define GNNA_CHAIN 1
 #endif
+#ifndef GNNA_CHAIN_IDS     // 32 ids per round trip
+#define GNNA_CHAIN_IDS GNNA_CHAIN
+#endif
+#ifndef GNNA_CHAIN_HOIST   // flush loads issued before the gather
+#define GNNA_CHAIN_HOIST GNNA_CHAIN
+#endif
 
 namespace gnna {
 
@@ -119,7 +125,7 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
     // variant also carries a weight per id and keeps the short batch (it is about rounding, not speed)
     constexpr int IPL_SHORT = (LPR >= 8) ? 1 : 8 / LPR;
     constexpr int IPL_LONG = (LPR >= 32) ? 1 : (32 / LPR > 8 ? 8 : 32 / LPR);
-    constexpr int IPL = (GNNA_CHAIN && !WEIGHTED) ? IPL_LONG : IPL_SHORT;
+    constexpr int IPL = (GNNA_CHAIN_IDS && !WEIGHTED) ? IPL_LONG : IPL_SHORT;
     constexpr int B = LPR * IPL;                     // neighbours per batch (>= 8)
     constexpr int U = (KCH >= 8) ? 1 : 8 / KCH;      // neighbour rows in flight per sub-warp
     static_assert(B % U == 0, "batch must be a multiple of the unroll");
@@ -162,13 +168,13 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
         for (int v = 0; v < VEC; v++) acc[k][v] = 0.f;
     }
 
-#if GNNA_CHAIN
+#if GNNA_CHAIN_IDS || GNNA_CHAIN_HOIST
     // what the flush needs, requested now: the answers arrive while the rows are gathered
     bool own = false;
     float mul = (flags & F_SCALE) ? scale : 1.f;
     {
         int r0 = 0, r1 = 0;
-        if (len > 0) {
+        if (GNNA_CHAIN_HOIST && len > 0) {
             r0 = ldg_keep(row_ptr + src);
             r1 = ldg_keep(row_ptr + src + 1);
             if (flags & F_ROWSCALE) mul = ldg_keep_f(degrees + src);
@@ -190,7 +196,7 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
         };
         fetch_ids(0);
         // plain store when this group is the node's whole adjacency list, else vector reduction
-        own = !(flags & F_ACCUMULATE) && (beg == r0) && (end == r1);
+        if (GNNA_CHAIN_HOIST) own = !(flags & F_ACCUMULATE) && (beg == r0) && (end == r1);
         for (int base = 0; base < maxlen; base += B) {
             if (base > 0) fetch_ids(base);
             // steps whose U neighbours every sub-warp of the warp still has need no predicates
@@ -203,6 +209,10 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
                     batch_step<T, VEC, LPR, KCH, U, IPL, WEIGHTED, true>(lane_base, row_bytes, nchunks, chunk0, j0, nid, wgt, acc);
                 }
             }
+        }
+        if (!GNNA_CHAIN_HOIST && len > 0) {
+            own = !(flags & F_ACCUMULATE) && (beg == __ldg(row_ptr + src)) && (end == __ldg(row_ptr + src + 1));
+            if (flags & F_ROWSCALE) mul = __ldg(degrees + src);
         }
     }
 #else
@@ -237,7 +247,7 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
 #endif
 
     if (len > 0) {
-#if !GNNA_CHAIN
+#if !(GNNA_CHAIN_IDS || GNNA_CHAIN_HOIST)
         // plain store when this group is the node's whole adjacency list, else vector reduction
         const bool own = !(flags & F_ACCUMULATE) && (beg == __ldg(row_ptr + src)) && (end == __ldg(row_ptr + src + 1));
         float mul = (flags & F_SCALE) ? scale : 1.f;

@@ -2,11 +2,12 @@
 
     python tools/ab_chain.py [--out gpurun_out/ab_chain.json] [--workloads reddit,ogbn-products] [--scale 1.0]
 
-A = the in-tree default library, B = gnnadvisor_osdi21_b200/libgnna_b200_nochain.so (built with
-`python -m gnnadvisor_osdi21_b200.build -DGNNA_CHAIN=0 --out=...`: the kernel before the dependent-load
-chain was shortened).  Both are called through the C ABI (include/gnna_b200.h) with the same pointers;
-results are compared element-wise, then each call is timed with CUDA events (3 warm-ups + 20 calls, A/B
-interleaved twice, best kept)."""
+A = the in-tree default library; B, C, D = variant builds next to it (tools/build_variants.sh):
+    B libgnna_b200_nochain.so  -DGNNA_CHAIN=0        the kernels before the dependent-load chain was shortened
+    C libgnna_b200_hoist.so    -DGNNA_CHAIN_IDS=0    flush loads hoisted only
+    D libgnna_b200_ids.so      -DGNNA_CHAIN_HOIST=0  32 ids per round trip only
+All are called through the C ABI (include/gnna_b200.h) with the same pointers; results are compared element-wise
+with B, then each call is timed with CUDA events (3 warm-ups + 20 calls, variants interleaved twice, best kept)."""
 import argparse
 import ctypes
 import json
@@ -48,10 +49,13 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab_chain.json"))
     ap.add_argument("--workloads", default="reddit,ogbn-products")
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--b-lib", default=os.path.join(ROOT, "gnnadvisor_osdi21_b200", "libgnna_b200_nochain.so"))
     args = ap.parse_args()
     dev = torch.device("cuda:0")
-    libs = {"A_default": bind(_lib.LIB_PATH), "B_nochain": bind(args.b_lib)}
+    pkg = os.path.join(ROOT, "gnnadvisor_osdi21_b200")
+    paths = {"A_default": _lib.LIB_PATH, "B_nochain": os.path.join(pkg, "libgnna_b200_nochain.so"),
+             "C_hoist": os.path.join(pkg, "libgnna_b200_hoist.so"), "D_ids": os.path.join(pkg, "libgnna_b200_ids.so")}
+    libs = {k: bind(v) for k, v in paths.items() if os.path.exists(v)}
+    assert "A_default" in libs and "B_nochain" in libs, "build the variants first (tools/build_variants.sh)"
     p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
     rows = []
     for wl in args.workloads.split(","):
@@ -84,18 +88,20 @@ def main():
                     2, p(Xb), 1, p(Wf), 0.5, p(o), p(xaggs["A_default"]), p(rp), p(ci), nul, p(pp), p(pn), N, D, D, P, 32, 32, 4, st)
             for cname, call in cases.items():
                 row = {"workload": wl, "N": N, "E": E, "D": D, "case": cname}
-                for k, lib in libs.items():
+                # the fused tile has two versions only (GNNA_CHAIN): C and D contain A's
+                use = {k: v for k, v in libs.items() if not cname.startswith("fused") or k[0] in "AB"}
+                for k, lib in use.items():
                     rc = call(lib, outs[k])
                     if rc != 0:
                         row[k + "_error"] = (lib.gnna_last_error() or b"?").decode()
                 torch.cuda.synchronize()
-                a, b = outs["A_default"], outs["B_nochain"]
-                row["max_rel_diff"] = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
-                best = {k: 1e30 for k in libs}
+                b = outs["B_nochain"]
+                row["max_rel_diff_vs_B"] = max(((outs[k] - b).abs().max() / b.abs().max().clamp_min(1e-30)).item() for k in use)
+                best = {k: 1e30 for k in use}
                 for _ in range(2):
-                    for k, lib in libs.items():
+                    for k, lib in use.items():
                         best[k] = min(best[k], timed(lambda: call(lib, outs[k])))
-                for k in libs:
+                for k in use:
                     row[k + "_ms"] = round(best[k], 4)
                 row["speedup_A_over_B"] = round(best["B_nochain"] / best["A_default"], 3)
                 rows.append(row)
@@ -104,7 +110,7 @@ def main():
         del gr, rp, ci, pp, pn, deg
         torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    json.dump({"A": _lib.LIB_PATH, "B": args.b_lib, "rows": rows}, open(args.out, "w"), indent=1)
+    json.dump({"libs": {k: paths[k] for k in libs}, "rows": rows}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
