@@ -396,8 +396,11 @@ def test_mixed_precision_gin_operators(din, dout):
 
 @pytest.mark.parametrize("model", ["gcn", "gin"])
 def test_mixed_precision_layers_train(model):
-    """GCNConv / GINConv(gather_dtype="bf16") in a 2-layer model: loss and weight gradients within 1e-2 of the fp32 layers."""
-    import torch.nn.functional as F
+    """GCNConv / GINConv(gather_dtype="bf16") in a 2-layer model with autograd: output and weight gradients within 1e-2
+    (relative to the largest element) of the fp32 layers.  The loss is a fixed random projection of the output, so the
+    gradients are well conditioned (nll_loss on near-uniform logits makes them sums of cancelling terms), and there is no
+    ReLU between the layers: a pre-activation that changes sign under a 2^-9 perturbation flips its whole gradient term,
+    which is a property of ReLU, not an error of the operators."""
     n, din, hid, cls = 1500, 32, 64, 41
     rp, ci = GRAPHS["rmat"]()
     g = G(rp, ci, 32)
@@ -409,7 +412,7 @@ def test_mixed_precision_layers_train(model):
     info.partPtr, info.part2Node = g.d_pp, g.d_pn
     info.partSize, info.dimWorker, info.warpPerBlock = 32, 32, 4
     x = dev(rand_features(n, din, 66))
-    y = torch.arange(n, device=DEV) % cls
+    R = dev(rand_features(n, cls, 70))
     res = {}
     for kind in ("fp32", "bf16"):
         torch.manual_seed(7)
@@ -417,13 +420,12 @@ def test_mixed_precision_layers_train(model):
         c1, c2 = conv(din, hid, gather_dtype=kind).to(DEV), conv(hid, cls, gather_dtype=kind).to(DEV)
         if model == "gin":
             c1.eplison = c2.eplison = 0.02           # keep activations O(1) (no degree normalisation in GIN)
-        loss = F.nll_loss(F.log_softmax(c2(F.relu(c1(x, info)), info), dim=1), y)
-        loss.backward()
-        res[kind] = (loss.item(), c1.weights.grad.cpu().numpy(), c2.weights.grad.cpu().numpy())
-    assert abs(res["bf16"][0] - res["fp32"][0]) <= 1e-2 * abs(res["fp32"][0])
-    for k in (1, 2):
+        h = c2(c1(x, info), info)
+        (h * R).sum().backward()
+        res[kind] = (h.detach().cpu().numpy(), c1.weights.grad.cpu().numpy(), c2.weights.grad.cpu().numpy())
+    for k, what in enumerate(("output", "grad of layer 1", "grad of layer 2")):
         ref = res["fp32"][k]
-        assert np.abs(res["bf16"][k] - ref).max() <= 1e-2 * np.abs(ref).max(), "grad of layer %d" % k
+        assert np.abs(res["bf16"][k] - ref).max() <= 1e-2 * np.abs(ref).max(), what
 
 
 # ------------------------------------------------------------------------------------------ autograd layers
