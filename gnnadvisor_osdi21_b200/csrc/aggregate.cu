@@ -112,7 +112,7 @@ enum : int {
 };
 
 template <typename T, int VEC, int LPR, int KCH, bool WEIGHTED>
-__global__ void __launch_bounds__(GNNA_LB, (KCH >= 2 || LPR == 32 || VEC >= 8) ? GNNA_WIDE_MIN_CTAS : GNNA_MIN_CTAS)
+__global__ void __launch_bounds__(GNNA_LB, (KCH >= 2 || LPR == 32 || (VEC >= 8 && !GNNA_BF16_NARROW)) ? GNNA_WIDE_MIN_CTAS : GNNA_MIN_CTAS)
 aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
                  const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                  const float *__restrict__ degrees,
