@@ -79,6 +79,7 @@ SIGNATURES = {
     "gnna_launch_count": (i64, [i32]),
     "gnna_set_gcn_exact": (i32, [i32]),
     "gnna_set_staged": (i32, [i32]),
+    "gnna_set_runs": (i32, [i32]),
 }
 
 _lib = None
@@ -120,3 +121,9 @@ def set_gcn_exact(on):
 def set_staged(on):
     """True: TMA-staged persistent aggregation kernel where it applies (csrc/aggregate_staged.cu)."""
     return bool(load().gnna_set_staged(1 if on else 0))
+
+
+def set_runs(run):
+    """run > 0: run-based software-pipelined aggregation kernel (csrc/aggregate_runs.cu), `run` groups per sub-warp;
+    0: the default kernel.  Returns the previous setting."""
+    return int(load().gnna_set_runs(int(run)))

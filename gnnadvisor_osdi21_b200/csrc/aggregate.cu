@@ -48,6 +48,9 @@
 #ifndef GNNA_WIDE_MIN_CTAS
 #define GNNA_WIDE_MIN_CTAS 2
 #endif
+#ifndef GNNA_BF16_NARROW   // 1: 128-bit bf16 rows (VEC = 8) with one chunk per lane also get the 3-CTA / 40-register budget
+#define GNNA_BF16_NARROW 0
+#endif
 // GNNA_CHAIN=1 shortens the dependent-load chain of one neighbour-group (table -> ids -> rows ... -> row_ptr):
 //   * the ids of up to 32 neighbours (a whole group at the default partSize) are fetched in ONE round trip
 //     instead of one round trip per 8 or 16 neighbours;
@@ -612,6 +615,16 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     if (staged_mode() && elem_bytes == 4 && !weighted && ldx == dim && g.gy == 1) {
         const int rc = aggregate_staged((const float *)X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
                                         (long long)num_parts, 0x7fffffffffffffffLL, dim, part_size, scale, flags, stream);
+        if (rc != GNNA_ERR_UNSUPPORTED) {
+            e = cudaSuccess;
+            if (rc != GNNA_OK) { release(); return rc; }
+            goto finish;
+        }
+    }
+    // opt-in: run-based software-pipelined kernel (aggregate_runs.cu)
+    if (runs_mode() > 0 && !weighted) {
+        const int rc = aggregate_runs(elem_bytes, X, o, row_ptr, col_idx, degrees, part_ptr, part2node, (long long)num_nodes,
+                                      (long long)num_parts, dim, ldx, scale, flags & (F_SCALE | F_ROWSCALE), stream);
         if (rc != GNNA_ERR_UNSUPPORTED) {
             e = cudaSuccess;
             if (rc != GNNA_OK) { release(); return rc; }

@@ -41,6 +41,13 @@ int aggregate_staged(const float *X, float *out, const int32_t *row_ptr, const i
                      const int32_t *part_ptr, const int32_t *part2node, long long num_parts, long long num_edges,
                      int dim, int part_size, float scale, int flags, cudaStream_t stream);
 
+// run-based software-pipelined variant (aggregate_runs.cu); `out` already zeroed; flags: 1 = scale, 2 = degrees[node];
+// GNNA_ERR_UNSUPPORTED when switched off (gnna_set_runs(0), the default) or the shape has no such variant
+int aggregate_runs(int elem_bytes, const void *X, float *out, const int32_t *row_ptr, const int32_t *col_idx,
+                   const float *degrees, const int32_t *part_ptr, const int32_t *part2node, long long num_nodes,
+                   long long num_parts, int dim, int ldx, float scale, int flags, cudaStream_t stream);
+int runs_mode();
+
 bool gcn_exact_mode();   // GNNA_GCN_EXACT / gnna_set_gcn_exact
 
 // Xs[i,:] = degrees[i] * X[i,:]  (X == Xs allowed)

@@ -648,3 +648,46 @@ def test_staged_tma_kernel(dim, ps):
                          oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="staged F6 exact=%s" % exact, terms=g.terms(0, X))
     finally:
         _lib.set_staged(prev)
+
+
+# ------------------------------------------------------------------------------------------ run-based pipelined kernel
+@pytest.mark.parametrize("dim", [8, 16, 32, 64, 100, 128])
+@pytest.mark.parametrize("run,ps", [(1, 32), (4, 32), (8, 3), (8, 64), (64, 32)])
+def test_run_based_kernel(dim, run, ps):
+    """csrc/aggregate_runs.cu: a sub-warp owns `run` consecutive groups, prefetches the next group's table entries and
+    ids, merges groups of one node in registers.  Same results as the oracle; rows that are one group stay bit-identical."""
+    from gnnadvisor_osdi21_b200 import _lib
+    prev = _lib.set_runs(run)
+    try:
+        for gname in ("rmat", "uniform"):
+            rp, ci = GRAPHS[gname]()
+            g = G(rp, ci, ps)
+            X = rand_features(g.n, dim, 70 + dim)
+            dX = dev(X)
+            assert_close(ops.SAG(dX, *g.gargs(), g.d_deg, *g.pargs(), ps, 32, 4).cpu().numpy(),
+                         oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="runs SAG", terms=g.terms(0, X))
+            assert_close(_gcn_agg(dX, g, 32, 4), oracle.aggregate(1, X, ci, g.deg, 1.0, g.pp, g.pn), what="runs GCN",
+                         terms=g.terms(1, X))
+            assert_close(_gin_agg(dX, g, 0.5, 32, 4), oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn), what="runs GIN",
+                         terms=g.terms(2, X))
+            if dim % 8 == 0:
+                Xb = torch.from_numpy(X).to(torch.bfloat16)
+                got = ops.aggregate_bf16(2, Xb.to(DEV), *g.gargs(), g.d_deg, 0.5, *g.pargs(), ps, 32, 4).cpu().numpy()
+                Xr = Xb.float().numpy()
+                assert_close(got, oracle.aggregate(2, Xr, ci, g.deg, 0.5, g.pp, g.pn), what="runs bf16 GIN", terms=g.terms(2, Xr))
+        # single-group rows stay bit-identical; F6 table (terminal 0), isolated nodes, last node isolated
+        rp, ci = make_graph("uniform", 3000, 20000, 33)
+        g = G(rp, ci, 64)
+        X = rand_features(g.n, dim, 71)
+        assert np.array_equal(_gin_agg(dev(X), g, 0.5, 32, 4), oracle.aggregate(2, X, ci, None, 0.5, g.pp, g.pn))
+        rng = np.random.default_rng(3)
+        deg = rng.integers(0, 50, 900); deg[::5] = 0; deg[-1] = 0; deg[-2] = 40
+        rp = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        ci = rng.integers(0, 900, rp[-1]).astype(np.int32)
+        X = rand_features(900, dim, 72)
+        for exact in (True, False):
+            g = G(rp, ci, 32, exact=exact)
+            assert_close(ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4).cpu().numpy(),
+                         oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="runs F6 exact=%s" % exact, terms=g.terms(0, X))
+    finally:
+        _lib.set_runs(prev)

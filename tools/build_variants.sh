@@ -6,5 +6,6 @@ P=gnnadvisor_osdi21_b200
 python -m $P.build -DGNNA_CHAIN=0 --out=$PWD/$P/libgnna_b200_nochain.so &
 python -m $P.build -DGNNA_CHAIN_IDS=0 --out=$PWD/$P/libgnna_b200_hoist.so &
 python -m $P.build -DGNNA_CHAIN_HOIST=0 --out=$PWD/$P/libgnna_b200_ids.so &
+python -m $P.build -DGNNA_BF16_NARROW=1 --out=$PWD/$P/libgnna_b200_bf16n.so &
 wait
 ls -la $P/*.so
