@@ -125,5 +125,5 @@ def set_staged(on):
 
 def set_runs(run):
     """run > 0: run-based software-pipelined aggregation kernel (csrc/aggregate_runs.cu), `run` groups per sub-warp;
-    0: the default kernel.  Returns the previous setting."""
+    0: never; -1 (default): the library chooses.  Returns the previous setting."""
     return int(load().gnna_set_runs(int(run)))

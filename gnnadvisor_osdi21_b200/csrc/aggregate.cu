@@ -621,8 +621,8 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
             goto finish;
         }
     }
-    // opt-in: run-based software-pipelined kernel (aggregate_runs.cu)
-    if (runs_mode() > 0 && !weighted) {
+    // run-based software-pipelined kernel (aggregate_runs.cu) where the library's rule or the caller selects it
+    if (runs_mode() != 0 && !weighted) {
         const int rc = aggregate_runs(elem_bytes, X, o, row_ptr, col_idx, degrees, part_ptr, part2node, (long long)num_nodes,
                                       (long long)num_parts, dim, ldx, scale, flags & (F_SCALE | F_ROWSCALE), stream);
         if (rc != GNNA_ERR_UNSUPPORTED) {

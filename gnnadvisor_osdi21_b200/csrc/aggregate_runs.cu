@@ -12,7 +12,8 @@
 //     groups costs ceil(k/R)+1 vector reductions instead of k.
 // The flush is always a vector reduction (`red.global.add.v4.f32`) into the zeroed output.
 // Supported: one 16-byte chunk per lane (dim <= 128 fp32 / 256 bf16 with 128-bit rows), unweighted modes (SAG, GIN,
-// pre-scaled GCN).  Everything else stays on aggregate.cu.  Selected by gnna_set_runs(R) / GNNA_RUNS=R (0 = off).
+// pre-scaled GCN).  Everything else stays on aggregate.cu.  gnna_set_runs(R) / GNNA_RUNS=R: R > 0 forces it, 0 switches
+// it off, -1 (default) lets the library choose (auto_runs below, from profiles/r01_v8_ab_runs.txt).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -23,7 +24,7 @@
 #define GNNA_RUNS_MIN_CTAS 4      // x 256 threads: 64 registers, 32 resident warps
 #endif
 #ifndef GNNA_RUNS_DEFAULT
-#define GNNA_RUNS_DEFAULT 0
+#define GNNA_RUNS_DEFAULT (-1)
 #endif
 
 namespace gnna {
@@ -142,16 +143,29 @@ aggregate_runs_kernel(const T *__restrict__ X, float *__restrict__ out, const in
     flush();
 }
 
-static int g_runs = -1;
+static int g_runs = -2;   // -2: not decided yet (environment), -1: auto, 0: off, R > 0: forced
 int runs_mode()
 {
-    if (g_runs < 0) {
+    if (g_runs < -1) {
         const char *e = getenv("GNNA_RUNS");
         g_runs = e ? atoi(e) : GNNA_RUNS_DEFAULT;
-        if (g_runs < 0) g_runs = 0;
+        if (g_runs < -1) g_runs = -1;
         if (g_runs > 64) g_runs = 64;
     }
     return g_runs;
+}
+
+// The library's own choice (measured on B200, profiles/r01_v8_ab_runs.txt).  The run-based kernel wins where nodes
+// have many groups (Reddit look-alike: 16 groups per node -- merged in registers, and nearly every group is full so
+// the speculative id prefetch is never wasted) and the default kernel is latency-bound: every bf16 width (12-23 %
+// faster, the 128-byte-row gather reaches the L2 port limit) and fp32 rows of 17..32 chunks (6 %).  On sparse graphs
+// (ogbn-products look-alike: 2 groups per node, HBM-bound) it is within +-5 % and loses at narrow rows: stay on the
+// default kernel.
+static int auto_runs(int elem_bytes, int nchunks, long long num_nodes, long long num_parts)
+{
+    if (num_parts < 4 * num_nodes) return 0;
+    if (elem_bytes == 2) return nchunks >= 8 ? 4 : 8;
+    return nchunks > 16 ? 4 : 0;
 }
 
 template <typename T, int VEC, int LPR>
@@ -177,14 +191,16 @@ int aggregate_runs(int elem_bytes, const void *X, float *out, const int32_t *row
                    const float *degrees, const int32_t *part_ptr, const int32_t *part2node, long long num_nodes,
                    long long num_parts, int dim, int ldx, float scale, int flags, cudaStream_t stream)
 {
-    const int run = runs_mode();
-    if (run <= 0) return GNNA_ERR_UNSUPPORTED;
+    int run = runs_mode();
+    if (run == 0) return GNNA_ERR_UNSUPPORTED;
     const int vec = 16 / elem_bytes;
     if (ldx % vec != 0 || dim % 4 != 0 || (((uintptr_t)X | (uintptr_t)out) & 15) || !row_ptr) return GNNA_ERR_UNSUPPORTED;
     const int nchunks = ldx / vec;
     int lpr = 4;
     while (lpr < nchunks) lpr *= 2;
     if (lpr > 32) return GNNA_ERR_UNSUPPORTED;
+    if (run < 0) run = auto_runs(elem_bytes, nchunks, num_nodes, num_parts);
+    if (run <= 0) return GNNA_ERR_UNSUPPORTED;
 #define GNNA_RUNS_CASE(TYPE, VEC, LPR)                                                                                   \
     return launch_runs<TYPE, VEC, LPR>(X, out, row_ptr, col_idx, degrees, part_ptr, part2node, num_nodes, num_parts, run, \
                                        dim, ldx, scale, flags, stream)
@@ -211,6 +227,6 @@ int aggregate_runs(int elem_bytes, const void *X, float *out, const int32_t *row
 extern "C" int gnna_set_runs(int run)
 {
     const int prev = gnna::runs_mode();
-    gnna::g_runs = run < 0 ? 0 : (run > 64 ? 64 : run);
+    gnna::g_runs = run < 0 ? -1 : (run > 64 ? 64 : run);
     return prev;
 }

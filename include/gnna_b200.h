@@ -294,11 +294,12 @@ GNNA_API int gnna_set_gcn_exact(int on);
  * B200 (the index streams are 1.5 % of the bytes), hence opt-in.                                       */
 GNNA_API int gnna_set_staged(int on);
 
-/* R > 0 = use the run-based software-pipelined kernel (csrc/aggregate_runs.cu) where it applies (unweighted modes,
- * 128-bit rows of at most 32 chunks): a sub-warp owns R consecutive neighbour-groups, prefetches the table entries
- * and ids of the next group while it gathers the rows of the current one, and merges groups of one node in registers.
- * 0 = the one-group-per-sub-warp kernel (csrc/aggregate.cu).  Also GNNA_RUNS=R in the environment.  Returns the
- * previous setting.                                                                                        */
+/* The run-based software-pipelined kernel (csrc/aggregate_runs.cu; unweighted modes, 128-bit rows of at most 32
+ * chunks): a sub-warp owns R consecutive neighbour-groups, prefetches the table entries and ids of the next group
+ * while it gathers the rows of the current one, and merges groups of one node in registers.
+ * R > 0 = use it with runs of R groups wherever it applies; 0 = never (always csrc/aggregate.cu);
+ * -1 (default) = the library chooses: graphs with >= 4 groups per node, bf16 rows (R = 4, or 8 below 8 chunks) and
+ * fp32 rows of 17..32 chunks (R = 4).  Also GNNA_RUNS=R in the environment.  Returns the previous setting.    */
 GNNA_API int gnna_set_runs(int run);
 
 /* Number of kernels this library has launched on this thread since the last reset

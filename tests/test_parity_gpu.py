@@ -691,3 +691,31 @@ def test_run_based_kernel(dim, run, ps):
                          oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="runs F6 exact=%s" % exact, terms=g.terms(0, X))
     finally:
         _lib.set_runs(prev)
+
+
+def test_run_based_kernel_auto_rule_on_a_dense_graph():
+    """Default setting (-1): the library routes bf16 rows and wide fp32 rows of graphs with >= 4 groups per node through
+    the run-based kernel (csrc/aggregate_runs.cu auto_runs).  Same tolerance as everywhere; also the mixed-precision
+    GCN operator on top of it with an odd width (padded bf16 rows)."""
+    from gnnadvisor_osdi21_b200 import _lib
+    assert _lib.set_runs(-1) == -1, "the default must be the library's own choice"
+    rp, ci = make_graph("rmat", 400, 120000, 81)          # ~300 neighbours per node: ~10 groups per node
+    g = G(rp, ci, 32)
+    assert len(g.pn) >= 4 * g.n
+    for dim in (16, 64, 128):
+        X = rand_features(g.n, dim, 82 + dim)
+        assert_close(ops.SAG(dev(X), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 4).cpu().numpy(),
+                     oracle.aggregate(0, X, ci, None, 1.0, g.pp, g.pn), what="auto SAG %d" % dim, terms=g.terms(0, X))
+        Xb = torch.from_numpy(X).to(torch.bfloat16)
+        Xr = Xb.float().numpy()
+        for mode in (0, 2):
+            got = ops.aggregate_bf16(mode, Xb.to(DEV), *g.gargs(), g.d_deg, 0.5, *g.pargs(), 32, 32, 4).cpu().numpy()
+            assert_close(got, oracle.aggregate(mode, Xr, ci, g.deg, 0.5, g.pp, g.pn), what="auto bf16 mode %d dim %d" % (mode, dim),
+                         terms=g.terms(mode, Xr))
+    X, W = rand_features(g.n, 24, 90), rand_weight(24, 41, 91)
+    y, = ops.forward_mixed(dev(X), dev(W), *g.gargs(), 1.0 / g.d_deg, *g.pargs(), 32, 32, 4)
+    inv = (1.0 / g.deg).astype(np.float32)
+    aX, aW = np.abs(X).astype(np.float64), np.abs(W).astype(np.float64)
+    ref = oracle.forward(X, W, rp, ci, inv, g.pp, g.pn)[0]
+    terms = oracle.aggregate(1, aX @ aW, ci, inv, 1.0, g.pp, g.pn)
+    assert_close(y.cpu().numpy(), ref, rtol=1e-2, what="auto mixed forward", terms=4 * terms)

@@ -51,7 +51,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab_chain.json"))
     ap.add_argument("--workloads", default="reddit,ogbn-products")
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--runs", default="4,8,16", help="run lengths of the run-based kernel to time (gnna_set_runs)")
+    ap.add_argument("--runs", default="-1,4,8", help="run lengths of the run-based kernel to time (gnna_set_runs)")
     ap.add_argument("--extra-libs", default="", help="name=path,... more variant builds")
     ap.add_argument("--dims", default="16,32,48,64,128")
     args = ap.parse_args()
@@ -66,8 +66,9 @@ def main():
     # the run-based kernel (csrc/aggregate_runs.cu) is a run-time switch of the default build: pseudo-variants of A
     runs_of = {k: 0 for k in libs}
     for r in (int(v) for v in args.runs.split(",") if v):
-        libs["A_runs%d" % r] = libs["A_default"]
-        runs_of["A_runs%d" % r] = r
+        name = "A_runs%d" % r if r > 0 else "A_auto"      # -1: the library's own rule
+        libs[name] = libs["A_default"]
+        runs_of[name] = r
     p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
     rows = []
     for wl in args.workloads.split(","):
@@ -129,6 +130,7 @@ def main():
             del X, Xb, outs
         del gr, rp, ci, pp, pn, deg
         torch.cuda.empty_cache()
+    libs["A_default"].gnna_set_runs(-1)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"libs": {k: paths.get(k, paths["A_default"] + " + gnna_set_runs(%d)" % runs_of[k]) for k in libs}, "rows": rows},
               open(args.out, "w"), indent=1)
