@@ -168,7 +168,7 @@ fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W
         auto prefetch_ids = [&](int from) {
 #pragma unroll
             for (int q = 0; q < IPL; q++) {
-                const int k = from + q * LPR + l;
+                const long long k = (long long)from + q * LPR + l;   // 64-bit: `from` may sit within 32 of INT_MAX
                 nid_n[q] = (k < e_limit) ? ldg_stream(col_idx + k) : -1;
             }
         };
