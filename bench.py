@@ -269,13 +269,14 @@ def run_single(args):
     peak, peak_src = peak_gbs()
     B = alg_bytes(E, N, D, P, prescale=True)
     achieved = B / (ms * 1e-3) / 1e9
-    traffic, l2_bytes = None, None
+    traffic, l2_bytes, l2_port = None, None, None
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tp) and args.scale == 1.0:
         try:
             prof = json.load(open(tp))
             traffic = prof.get("%s_D%d_f32" % (args.workload, D))
             l2_bytes = prof.get("%s_D%d_f32_l2_to_sm_bytes" % (args.workload, D))
+            l2_port = prof.get("%s_D%d_f32_l2_port_pct" % (args.workload, D))
         except Exception:   # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -284,8 +285,10 @@ def run_single(args):
                 "dram_GBs": (traffic / (ms * 1e-3) / 1e9) if traffic else None,
                 "dram_frac": (traffic / (ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "l2_to_sm_GBs": (l2_bytes / (ms * 1e-3) / 1e9) if l2_bytes else None,
+                "l2_port_pct_of_peak_ncu": l2_port,
                 "note": "step = cudaMemsetAsync(out) + prescale_rows + aggregate_kernel, timed together; features (%.0f MB) fit in L2, so "
-                        "achieved may exceed the HBM copy peak -- see traffic (ncu dram bytes per launch)" % (N * D * 4 / 1e6)}
+                        "achieved may exceed the HBM copy peak -- see traffic (ncu dram bytes per launch); the binding unit is then the "
+                        "L2 -> SM port (l2_port_pct_of_peak_ncu, from the committed ncu capture of this kernel)" % (N * D * 4 / 1e6)}
 
     # ---- end to end through the public API with host buffers
     # the aggregation-only entry of the C ABI (gnna_gcn_aggregate_f32, the kernel behind

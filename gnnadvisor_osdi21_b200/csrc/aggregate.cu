@@ -512,15 +512,15 @@ int scale_rows_bf16(const float *X, void *Xb, const float *degrees, int64_t num_
 // stream-ordered scratch: keep freed blocks in the pool instead of returning them to the OS at every sync
 static int scratch_alloc(float **p, size_t bytes, cudaStream_t stream)
 {
-    static bool pool_ready = false;
-    if (!pool_ready) {
-        int dev = 0;
+    static bool pool_ready[64] = {false};   // per device: a process may drive several GPUs
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_ready[dev]) {
         cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long keep = ~0ULL;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        pool_ready = true;
+        pool_ready[dev] = true;
     }
     GNNA_CUDA_CHECK(cudaMallocAsync((void **)p, bytes, stream));
     return GNNA_OK;

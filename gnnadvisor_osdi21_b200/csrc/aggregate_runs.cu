@@ -155,17 +155,21 @@ int runs_mode()
     return g_runs;
 }
 
-// The library's own choice (measured on B200, profiles/r01_v8_ab_runs.txt).  The run-based kernel wins where nodes
-// have many groups (Reddit look-alike: 16 groups per node -- merged in registers, and nearly every group is full so
-// the speculative id prefetch is never wasted) and the default kernel is latency-bound: every bf16 width (12-23 %
-// faster, the 128-byte-row gather reaches the L2 port limit) and fp32 rows of 17..32 chunks (6 %).  On sparse graphs
-// (ogbn-products look-alike: 2 groups per node, HBM-bound) it is within +-5 % and loses at narrow rows: stay on the
-// default kernel.
+// The library's own choice (measured on B200, profiles/r01_v8_ab_runs.txt, r01_v9_ab_auto.txt).
+//   * dense graphs (>= 4 groups per node, e.g. the Reddit look-alike with 16: groups are merged in registers and nearly
+//     every group is full, so the speculative id prefetch is never wasted): every bf16 width (12-23 % faster; the
+//     128-byte-row gather reaches the L2 port limit) and fp32 rows that are not exactly one or two 128-byte lines
+//     (4, 12, 32 chunks: 3-6 %; at 8 and 16 chunks the default kernel already sits at the L2 port limit);
+//   * sparse graphs (ogbn-products look-alike: 2 groups per node, HBM-bound): bf16 rows of >= 6 chunks only (3-6 %);
+//     narrow rows lose up to 15 % there (prefetch wasted on partial groups) and fp32 is within +-3 %.
 static int auto_runs(int elem_bytes, int nchunks, long long num_nodes, long long num_parts)
 {
-    if (num_parts < 4 * num_nodes) return 0;
-    if (elem_bytes == 2) return nchunks >= 8 ? 4 : 8;
-    return nchunks > 16 ? 4 : 0;
+    const bool dense = num_parts >= 4 * num_nodes;
+    if (elem_bytes == 2) {
+        if (dense) return nchunks >= 8 ? 4 : 8;
+        return nchunks >= 6 ? 4 : 0;
+    }
+    return (dense && nchunks != 8 && nchunks != 16) ? 4 : 0;
 }
 
 template <typename T, int VEC, int LPR>

@@ -298,8 +298,9 @@ GNNA_API int gnna_set_staged(int on);
  * chunks): a sub-warp owns R consecutive neighbour-groups, prefetches the table entries and ids of the next group
  * while it gathers the rows of the current one, and merges groups of one node in registers.
  * R > 0 = use it with runs of R groups wherever it applies; 0 = never (always csrc/aggregate.cu);
- * -1 (default) = the library chooses: graphs with >= 4 groups per node, bf16 rows (R = 4, or 8 below 8 chunks) and
- * fp32 rows of 17..32 chunks (R = 4).  Also GNNA_RUNS=R in the environment.  Returns the previous setting.    */
+ * -1 (default) = the library chooses from its measurements (aggregate_runs.cu auto_runs): on graphs with >= 4 groups
+ * per node every bf16 width and the fp32 widths that are not whole 128-byte lines; on sparser graphs bf16 rows of >= 6
+ * chunks.  Also GNNA_RUNS=R in the environment.  Returns the previous setting.                                  */
 GNNA_API int gnna_set_runs(int run);
 
 /* Number of kernels this library has launched on this thread since the last reset
