@@ -105,6 +105,8 @@ LOOKALIKES = {
     "reddit":         (232965,      114615892,   602,  64,  41, "rmat"),
     "ogbn-products":  (2449029,     123718280,   100,  64,  47, "rmat"),
     "amazon0505":     (410236,      4878874,     96,   16,  22, "rmat"),
+    # config #5; use scale < 1 on a single GPU (the full graph is 1.6 G edges: sharded)
+    "ogbn-papers100M": (111059956,  1615685872,  128,  128, 172, "rmat"),
 }
 
 
