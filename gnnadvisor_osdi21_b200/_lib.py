@@ -80,6 +80,7 @@ SIGNATURES = {
     "gnna_set_gcn_exact": (i32, [i32]),
     "gnna_set_staged": (i32, [i32]),
     "gnna_set_runs": (i32, [i32]),
+    "gnna_query_runs": (i32, [i32, i32, i64, i64]),
 }
 
 _lib = None
@@ -127,3 +128,8 @@ def set_runs(run):
     """run > 0: run-based software-pipelined aggregation kernel (csrc/aggregate_runs.cu), `run` groups per sub-warp;
     0: never; -1 (default): the library chooses.  Returns the previous setting."""
     return int(load().gnna_set_runs(int(run)))
+
+
+def query_runs(elem_bytes, row_elems, num_nodes, num_parts):
+    """Run length the library would use for this shape (0: the one-group-per-sub-warp kernel).  Host-only."""
+    return int(load().gnna_query_runs(int(elem_bytes), int(row_elems), int(num_nodes), int(num_parts)))

@@ -228,6 +228,18 @@ int aggregate_runs(int elem_bytes, const void *X, float *out, const int32_t *row
 
 }  // namespace gnna
 
+// run length the library would use for a call of this shape under the current setting (0 = csrc/aggregate.cu)
+extern "C" int gnna_query_runs(int elem_bytes, int row_elems, int64_t num_nodes, int64_t num_parts)
+{
+    if ((elem_bytes != 4 && elem_bytes != 2) || row_elems <= 0) return 0;
+    const int vec = 16 / elem_bytes;
+    if (row_elems % vec != 0) return 0;
+    const int nchunks = row_elems / vec;
+    if (nchunks > 32) return 0;
+    const int run = gnna::runs_mode();
+    return run < 0 ? gnna::auto_runs(elem_bytes, nchunks, num_nodes, num_parts) : run;
+}
+
 extern "C" int gnna_set_runs(int run)
 {
     const int prev = gnna::runs_mode();

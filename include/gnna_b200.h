@@ -302,6 +302,10 @@ GNNA_API int gnna_set_staged(int on);
  * per node every bf16 width and the fp32 widths that are not whole 128-byte lines; on sparser graphs bf16 rows of >= 6
  * chunks.  Also GNNA_RUNS=R in the environment.  Returns the previous setting.                                  */
 GNNA_API int gnna_set_runs(int run);
+/* The run length a call of this shape would get under the current setting (0 = csrc/aggregate.cu): row_elems = row
+ * stride of the gathered matrix in elements (after padding: fp32 rows are padded to a multiple of 4, bf16 rows of the
+ * mixed operators to a multiple of 8).  Host-only, no GPU needed.                                            */
+GNNA_API int gnna_query_runs(int elem_bytes, int row_elems, int64_t num_nodes, int64_t num_parts);
 
 /* Number of kernels this library has launched on this thread since the last reset
  * (bench.py's "gpu_launches" is read from here, not guessed). */

@@ -213,3 +213,26 @@ def test_b200_decider_choices():
     p.decider_b200()
     assert (p.partSize, p.dimWorker_input, p.dimWorker_hidden, p.warpPerBlock_input) == (32, 16, 8, 4)
     assert ds.reordered == 1 and p.reorder_status
+
+
+def test_run_based_kernel_rule_and_switch():
+    """gnna_set_runs / gnna_query_runs (host-only): default = the library's rule from the B200 measurements
+    (csrc/aggregate_runs.cu auto_runs): dense graphs -> every bf16 width and fp32 rows that are not whole 128-byte
+    lines; sparse graphs -> bf16 rows of >= 6 chunks; forced / forbidden settings override it."""
+    from gnnadvisor_osdi21_b200 import _lib
+    prev = _lib.set_runs(-1)
+    try:
+        reddit = (232965, 3696299)            # ~16 groups per node
+        products = (2449029, 4900000)         # ~2 groups per node
+        q = _lib.query_runs
+        assert q(4, 64, *reddit) == 0 and q(4, 32, *reddit) == 0          # 256- and 128-byte fp32 rows: default kernel
+        assert q(4, 128, *reddit) == 4 and q(4, 48, *reddit) == 4 and q(4, 16, *reddit) == 4
+        assert q(2, 64, *reddit) == 4 and q(2, 128, *reddit) == 4 and q(2, 16, *reddit) == 8
+        assert q(4, 64, *products) == 0 and q(4, 128, *products) == 0
+        assert q(2, 64, *products) == 4 and q(2, 32, *products) == 0
+        assert q(4, 41, *reddit) == 0 and q(2, 100, *reddit) == 0         # not whole 16-byte chunks: not eligible
+        assert q(4, 256, *reddit) == 0                                    # more than 32 chunks per row
+        assert _lib.set_runs(0) == -1 and q(2, 64, *reddit) == 0
+        assert _lib.set_runs(8) == 0 and q(4, 64, *products) == 8
+    finally:
+        _lib.set_runs(prev)
