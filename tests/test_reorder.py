@@ -1,6 +1,10 @@
 """Vertex reordering (rabbit replacement): a valid permutation, applied consistently, that improves
 locality on graphs with community structure.  CPU only (host code of the C-ABI library)."""
+import os
+import sys
+
 import numpy as np
+import pytest
 import torch
 
 from gnnadvisor_osdi21_b200 import reorder as R
@@ -79,3 +83,42 @@ def test_compat_modules_export_the_reference_names():
         sys.path.remove(compat)
         for name in ("GNNAdvisor", "rabbit", "dgl", "torch_sparse"):
             sys.modules.pop(name, None)
+
+
+REF_PY = "/root/reference/GNNAdvisor"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PY), reason="the reference tree is only mounted in the authoring container")
+def test_reference_modules_import_unchanged_against_the_compat_modules():
+    """The reference's own gnn_conv.py / param.py / dataset.py, imported UNCHANGED from the read-only reference tree with
+    compat/ on the path (INTEGRATION.md option A): `import GNNAdvisor`, `import rabbit`, `import dgl` resolve to this
+    repository, the layer classes construct, and a call reaches our CHECK_INPUT (same message as GNNAdvisor.cpp:71-73)
+    with the reference's own positional argument order.  No GPU needed: CPU tensors are what CHECK_INPUT rejects."""
+    import importlib
+    import types
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnnadvisor_osdi21_b200", "compat")
+    names = ("GNNAdvisor", "rabbit", "dgl", "torch_sparse", "gnn_conv", "param", "dataset")
+    saved = {n: sys.modules.pop(n) for n in names if n in sys.modules}
+    sys.path[:0] = [compat, REF_PY]
+    try:
+        gnn_conv = importlib.import_module("gnn_conv")
+        assert gnn_conv.__file__.startswith(REF_PY)
+        assert os.path.dirname(gnn_conv.GNNA.__file__) == compat
+        importlib.import_module("dataset")                      # needs dgl + rabbit stand-ins at import time
+        info = types.SimpleNamespace(row_pointers=torch.zeros(5, dtype=torch.int32), column_index=torch.zeros(0, dtype=torch.int32),
+                                     degrees=torch.ones(4), partPtr=torch.zeros(1, dtype=torch.int32),
+                                     part2Node=torch.zeros(0, dtype=torch.int32), partSize=32, dimWorker=16, warpPerBlock=4)
+        X = torch.randn(4, 3)
+        for layer in (gnn_conv.GCNConv(3, 2), gnn_conv.GINConv(3, 2)):
+            with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+                layer(X, info)
+        with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+            gnn_conv.ScatterAndGather.apply(X, info)
+        # build_part on the host returns what GNNA_main.py:102-110 expects: two tensors whose .int() is the table
+        pp, pn = gnn_conv.GNNA.build_part(2, torch.tensor([0, 3, 3, 4], dtype=torch.int32))
+        assert pp.int().tolist() == [0, 2, 3, 4] and pn.int().tolist() == [0, 0, 2]
+    finally:
+        del sys.path[:2]
+        for n in names:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved)
