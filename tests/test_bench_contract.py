@@ -1,0 +1,42 @@
+"""bench.py's contract, as far as it can be checked without a GPU: the reference arm runs on the host cores alone and
+prints ONE JSON line with the keys the driver reads; the algorithmic-bytes formula is SURVEY.md 8(d)'s."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_on_cpu():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cora", "--dim", "16",
+                          "--steps", "2", "--warmup", "1", "--cpu-seconds", "2"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "edge*dim/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["vs_baseline"] is None and line["data"] == "synthetic"
+    assert line["config"]["num_nodes"] == 2708 and "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "cora",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_algorithmic_bytes_formula():
+    sys.path.insert(0, ROOT)
+    import bench
+    E, N, D, P = 114615892, 232965, 64, 3696299
+    # E*(D*s_x + 4) + N*(D*s_y + 8) + (2P+1)*4
+    assert bench.alg_bytes(E, N, D, P) == E * (D * 4 + 4) + N * (D * 4 + 8) + (2 * P + 1) * 4
+    assert bench.alg_bytes(E, N, D, P, sx=2) == E * (D * 2 + 4) + N * (D * 4 + 8) + (2 * P + 1) * 4
+    assert bench.alg_bytes(E, N, D, P, gcn=True) - bench.alg_bytes(E, N, D, P) == 4 * E
+    assert bench.alg_bytes(E, N, D, P, prescale=True) - bench.alg_bytes(E, N, D, P) == 2 * N * D * 4
