@@ -149,33 +149,52 @@ def build_workload(args, device):
     return gr, rp, ci, pp, pn, deg, X
 
 
-def config_of(args, N, E, P, extra=None):
-    c = {"workload": "%s look-alike GCN aggregation (synthetic rmat, symmetric): N=%d E=%d D=%d fp32" % (args.workload, N, E, args.dim),
+def config_of(args, N, E, P, world=1):
+    """The workload description.  A pure function of the command line and the (device-independent, seeded) graph, so the
+    --impl reference arm prints the same dict at every N."""
+    from gnnadvisor_osdi21_b200 import graph
+    from gnnadvisor_osdi21_b200.dist import default_row_weight
+    kind = graph.LOOKALIKES[args.workload][5]
+    c = {"workload": "%s look-alike GCN aggregation (synthetic %s, symmetric): N=%d E=%d D=%d fp32" % (args.workload, kind, N, E, args.dim),
          "num_nodes": N, "num_edges": E, "dim": args.dim, "num_parts": P,
          "partSize": args.part_size, "dimWorker": args.dim_worker, "warpPerBlock": args.warp_per_block,
          "scale": args.scale,
+         "generator": "counter-based pair stream (splitmix64), seed 20211, R-MAT %s" % (graph.RMAT_DEFAULT,) if kind == "rmat"
+                      else "counter-based pair stream (splitmix64), seed 20211, uniform",
          "l2": "inputs (col_idx %.0f MB + features %.0f MB + group table %.0f MB) %s; no flush between steps"
                % (E * 4 / 1e6, N * args.dim * 4 / 1e6, (2 * P + 1) * 4 / 1e6,
                   "exceed the 126 MB L2" if (E * 4 + N * args.dim * 4 + (2 * P + 1) * 4) > 126e6
                   else "FIT in the 126 MB L2 (a launch-latency-bound configuration, not a bandwidth measurement)")}
-    if extra:
-        c.update(extra)
+    if world > 1:
+        c["parallelism"] = ("1-D vertex-range shards x%d (cost-balanced: edges + %d per row), one halo exchange per aggregation"
+                            % (world, int(os.environ.get("GNNA_ROW_WEIGHT", default_row_weight(world)))))
     return c
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_pass(args, rp, ci, pp, pn, deg, X, seconds):
-    """Time the oracle (OpenMP port of the reference algorithm) on all host cores; bounded by `seconds`."""
+def host_threads():
+    """Every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its children; the CPU legs set the
+    thread count explicitly so the baseline is the same at every N."""
+    return len(os.sched_getaffinity(0))
+
+
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
+    return oracle
+
+
+def cpu_pass(args, rp, ci, pp, pn, deg, X, seconds):
+    """Time the oracle (OpenMP port of the reference algorithm) on all host cores.  The whole graph when one pass fits the
+    `seconds` budget three times over, else the first groups (whole nodes) that do."""
+    oracle = _oracle()
+    threads = host_threads()
     rpn, cin, ppn, pnn = rp.cpu().numpy(), ci.cpu().numpy(), pp.cpu().numpy(), pn.cpu().numpy()
     degn, Xn = deg.cpu().numpy(), X.cpu().numpy()
     E, D = len(cin), Xn.shape[1]
-    cores = len(os.sched_getaffinity(0))
-    # sample = the first `frac` of the groups (whole nodes), sized from one quick probe
     probe_groups = min(len(pnn), 200_000)
     t = time.perf_counter()
-    oracle.aggregate(1, Xn, cin, degn, 1.0, ppn[:probe_groups + 1], pnn[:probe_groups], threads=-1)
+    oracle.aggregate(1, Xn, cin, degn, 1.0, ppn[:probe_groups + 1], pnn[:probe_groups], threads=threads)
     dt = time.perf_counter() - t
     per_group = dt / max(probe_groups, 1)
     groups = int(min(len(pnn), max(probe_groups, seconds / 3 / max(per_group, 1e-12))))
@@ -185,35 +204,52 @@ def cpu_pass(args, rp, ci, pp, pn, deg, X, seconds):
     best = None
     for _ in range(3):
         t = time.perf_counter()
-        oracle.aggregate(1, Xn, cin, degn, 1.0, ppn[:groups + 1], pnn[:groups], threads=-1)
+        oracle.aggregate(1, Xn, cin, degn, 1.0, ppn[:groups + 1], pnn[:groups], threads=threads)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
-    return {"value": edges * D / best, "unit": "edge*dim/s", "cores": cores, "kind": "port",
+    return {"value": edges * D / best, "unit": "edge*dim/s", "cores": threads, "kind": "port",
             "sample": "first %d of %d neighbour-groups (%d of %d edges) of the same graph, D=%d, best of 3, %d OpenMP threads"
-                      % (groups, len(pnn), edges, E, D, oracle.num_threads()),
-            "seconds": best}
+                      % (groups, len(pnn), edges, E, D, threads),
+            "seconds": best, "threads": threads, "groups_sampled": groups}
 
 
 def run_reference_arm(args):
+    """--impl reference: the CPU port of the reference algorithm (oracle/, the reference has no CPU path of its own:
+    SURVEY.md F8) on every host core, on the same seeded graph as our arm.  Never touches the GPU or libgnna_b200.so;
+    under torchrun rank 0 alone works.  One step = one pass over the WHOLE graph."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
-    gr, rp, ci, pp, pn, deg, X = build_workload(args, device) if device.type == "cuda" else _cpu_workload(args)
-    N, E, P = gr["num_nodes"], ci.numel(), pn.numel()
-    vals = []
-    per = max(2.0, min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1)))
-    for i in range(args.warmup + args.steps):
-        r = cpu_pass(args, rp, ci, pp, pn, deg, X, per)
-        if i >= args.warmup:
-            vals.append(r)
-    v = float(np.mean([r["value"] for r in vals]))
+    threads = host_threads()
+    torch.set_num_threads(threads)                 # graph construction below is torch-on-CPU
+    oracle = _oracle()
+    gr, rp, ci, pp, pn, deg, X = _cpu_workload(args)
+    N, E, P, D = gr["num_nodes"], ci.numel(), pn.numel(), args.dim
+    rpn, cin, ppn, pnn, degn, Xn = rp.numpy(), ci.numpy(), pp.numpy(), pn.numpy(), deg.numpy(), X.numpy()
+    # a full pass must fit the "few minutes" budget: bound the number of passes, never the graph
+    t = time.perf_counter()
+    oracle.aggregate(1, Xn, cin, degn, 1.0, ppn, pnn, threads=threads)
+    one = time.perf_counter() - t
+    steps = max(1, min(args.steps, int(120.0 / max(one, 1e-6))))
+    warm = max(1, min(args.warmup, int(30.0 / max(one, 1e-6))))
+    for _ in range(warm):
+        oracle.aggregate(1, Xn, cin, degn, 1.0, ppn, pnn, threads=threads)
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        oracle.aggregate(1, Xn, cin, degn, 1.0, ppn, pnn, threads=threads)
+        times.append(time.perf_counter() - t)
+    sec = float(np.mean(times))
+    v = E * D / sec
     line = {"impl": "reference", "metric": "aggregation throughput (GCN SpMM), edges*dim/s", "value": v, "unit": "edge*dim/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(np.mean([r["seconds"] for r in vals]) * 1e3), "higher_is_better": True,
+            "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_of(args, N, E, P),
-            "cpu_baseline": dict(vals[-1], value=v),
+            "config": config_of(args, N, E, P, world=args.gpus),
+            "cpu_baseline": {"value": v, "unit": "edge*dim/s", "cores": threads, "kind": "port", "threads": threads,
+                             "sample": "all %d neighbour-groups (%d edges) of the same graph, D=%d, mean of %d passes after %d warm-up, "
+                                       "%d OpenMP threads (set explicitly)" % (P, E, D, steps, warm, threads),
+                             "seconds": sec, "groups_sampled": P, "steps_run": steps},
             "e2e": {"value": v, "unit": "edge*dim/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -221,8 +257,7 @@ def run_reference_arm(args):
 
 def _cpu_workload(args):
     from gnnadvisor_osdi21_b200 import graph
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
+    oracle = _oracle()
     gr = graph.lookalike(args.workload, device="cpu", scale=args.scale)
     rp, ci = gr["row_ptr"], gr["col_idx"]
     pp, pn = oracle.build_part(args.part_size, rp.numpy(), exact=True)

@@ -277,8 +277,8 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
 // i.e. 2N/E of the gather traffic.
 template <int VEC>
 __global__ void __launch_bounds__(256)
-repack_rows_kernel(const float *__restrict__ X, float *__restrict__ Xs, const float *__restrict__ degrees,
-                   long long num_nodes, int dim, int ldx)
+repack_rows_kernel(const float *X, float *Xs, const float *__restrict__ degrees,
+                   long long num_nodes, int dim, int ldx)   // X == Xs is allowed (in-place pre-scale): no __restrict__, no ld.nc on X
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     if constexpr (VEC == 4) {   // dim == ldx, both 16-byte aligned
@@ -286,7 +286,7 @@ repack_rows_kernel(const float *__restrict__ X, float *__restrict__ Xs, const fl
         const long long total = num_nodes * cpr;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
             const float n = degrees ? __ldg(degrees + i / cpr) : 1.f;
-            float4 v = __ldg(reinterpret_cast<const float4 *>(X) + i);
+            float4 v = reinterpret_cast<const float4 *>(X)[i];
             v.x = __fmul_rn(n, v.x); v.y = __fmul_rn(n, v.y); v.z = __fmul_rn(n, v.z); v.w = __fmul_rn(n, v.w);
             reinterpret_cast<float4 *>(Xs)[i] = v;
         }
@@ -297,7 +297,7 @@ repack_rows_kernel(const float *__restrict__ X, float *__restrict__ Xs, const fl
             const int c = (int)(i - r * ldx);
             float v = 0.f;
             if (c < dim) {
-                v = __ldg(X + r * dim + c);
+                v = X[r * dim + c];
                 if (degrees) v = __fmul_rn(__ldg(degrees + r), v);
             }
             Xs[i] = v;
@@ -509,20 +509,26 @@ int scale_rows_bf16(const float *X, void *Xb, const float *degrees, int64_t num_
     return GNNA_OK;
 }
 
-// stream-ordered scratch: keep freed blocks in the pool instead of returning them to the OS at every sync
+// stream-ordered scratch from a PRIVATE pool per device: freed blocks up to 1 GiB stay in the pool for the next call
+// (no OS round trip per aggregation), anything beyond goes back to the driver at the next synchronisation, and the
+// process-wide default pool -- which other libraries and torch's cudaMallocAsync backend share -- is left alone.
 static int scratch_alloc(float **p, size_t bytes, cudaStream_t stream)
 {
-    static bool pool_ready[64] = {false};   // per device: a process may drive several GPUs
+    static cudaMemPool_t pools[64] = {nullptr};
     int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_ready[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        pool_ready[dev] = true;
+    GNNA_CUDA_CHECK(cudaGetDevice(&dev));
+    GNNA_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        GNNA_CUDA_CHECK(cudaMemPoolCreate(&pools[dev], &props));
+        unsigned long long keep = 1ULL << 30;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    GNNA_CUDA_CHECK(cudaMallocAsync((void **)p, bytes, stream));
+    GNNA_CUDA_CHECK(cudaMallocFromPoolAsync((void **)p, bytes, pools[dev], stream));
     return GNNA_OK;
 }
 

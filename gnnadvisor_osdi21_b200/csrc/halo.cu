@@ -9,7 +9,8 @@
 // the aggregation kernel on [own rows | halo rows] unchanged.  Halo buffers are double-buffered by step
 // parity; a producer may overwrite parity b only after the consumer acknowledged the step that last
 // read it (ack counters, also in peer memory), so no rank can run more than one step ahead.
-// All waits are bounded (about 4 s of GPU clock) and report through an error word instead of hanging.
+// All waits are bounded (about 4 s of GPU clock) and report through an error word instead of hanging; a producer that
+// gave up poisons the consumer's error word too, so stale halo rows are never consumed silently.
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
@@ -28,6 +29,7 @@ constexpr long long SPIN_LIMIT_CYCLES = 8000000000LL;   // ~4 s at 2 GHz
 struct HaloPushParams {
     float *peer_base[MAX_PEERS];          // the peer's feature buffer for this step parity (mapped)
     unsigned *peer_flag[MAX_PEERS];       // &flags[my_rank] inside the peer's control block
+    unsigned *peer_err[MAX_PEERS];        // the peer's error word: poisoned when I could not deliver its rows
     const unsigned *ack_from[MAX_PEERS];  // &acks[peer] inside MY control block (written by the peer)
     long long dst_row0[MAX_PEERS];        // row of the peer's buffer where my block of rows starts
     int send_lo[MAX_PEERS];               // my send list for the peer is send_idx[send_lo .. send_hi)
@@ -66,7 +68,15 @@ halo_push_kernel(const float *__restrict__ x_local, const long long *__restrict_
             if (step > 2) {
                 const long long t0 = clock64();
                 while (ld_acquire_sys(prm.ack_from[p]) + 2 < step) {
-                    if (clock64() - t0 > SPIN_LIMIT_CYCLES) { ok = 0; atomicExch(prm.error_word, 1u); break; }
+                    if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+                        // the rows are NOT delivered: say so on both sides.  The flag below still goes up so the
+                        // consumer does not spin as well, but its error word now reads 3 ("halo rows of this step are
+                        // stale") -- PeerHalo.error() / ShardedGraph.check() turn that into an exception on the host.
+                        ok = 0;
+                        atomicExch(prm.error_word, 1u);
+                        st_release_sys(prm.peer_err[p], 3u);
+                        break;
+                    }
                 }
             }
             s_ok = ok;
@@ -219,6 +229,7 @@ extern "C" int gnna_halo_push_f32(const float *x_local, const int64_t *send_idx,
         prm.send_hi[sl] = send_begin_host[p + 1];
         prm.peer_base[sl] = (float *)peer_feature_base_host[p];
         prm.peer_flag[sl] = (unsigned *)peer_ctrl_host[p] + my_rank;
+        prm.peer_err[sl] = (unsigned *)peer_ctrl_host[p] + 48;
         prm.ack_from[sl] = ctrl + 16 + p;
         prm.dst_row0[sl] = peer_dst_row0_host[p];
     }

@@ -157,6 +157,16 @@ extern "C" int gnna_prescale_rows_f32(const float *X, float *Xs, const float *de
     return prescale_rows(X, Xs, degrees, num_rows, dim, (cudaStream_t)stream);
 }
 
+// Row-major C[m,n] = op(A) * op(B) on the library's cuBLAS handle (fp32, TF32 off): the dense products of the layer
+// operators for callers that compose a layer themselves (the sharded layers do: product, halo exchange, aggregation).
+extern "C" int gnna_sgemm_f32(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
+                              const float *A, const float *B, float *C, void *stream)
+{
+    GNNA_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gnna_sgemm_f32: negative size");
+    GNNA_REQUIRE(m == 0 || n == 0 || (C && (k == 0 || (A && B))), "gnna_sgemm_f32: null pointer");
+    return sgemm_rm((cudaStream_t)stream, trans_a != 0, trans_b != 0, m, n, k, A, B, C);
+}
+
 #define GNNA_TRY(expr)             \
     do {                           \
         int _rc = (expr);          \

@@ -54,6 +54,11 @@ def _a2a(out, inp, out_splits, in_splits, group):
         dist.all_to_all_single(out, inp, out_splits, in_splits, group=group)
         return
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if out.is_cuda:      # gloo has no CUDA point-to-point: stage through the host (tests that run the CUDA kernels
+        o_h = torch.empty(out.shape, dtype=out.dtype)          # of several ranks on ONE GPU use this)
+        _a2a(o_h, inp.cpu(), out_splits, in_splits, group)
+        out.copy_(o_h)
+        return
     ooff = [0]
     ioff = [0]
     for s in out_splits:
@@ -77,21 +82,46 @@ class ShardedGraph:
     """This rank's shard of a graph every rank can see (replicated CSR in, sharded tables out)."""
 
     def __init__(self, row_ptr, col_idx, part_size, device=None, group=None, ranges=None, row_weight=0):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        device = torch.device(device) if device is not None else row_ptr.device
+        ranges = ranges if ranges is not None else partition_ranges(row_ptr, world, row_weight)
+        v0, v1 = ranges[rank], ranges[rank + 1]
+        e0, e1 = int(row_ptr[v0]), int(row_ptr[v1])
+        rp_local = (row_ptr[v0:v1 + 1].to(torch.int64) - e0).to(device)
+        self._setup(ranges, rp_local, col_idx[e0:e1].to(device), part_size, device, group,
+                    num_nodes_global=row_ptr.numel() - 1, num_edges_global=int(row_ptr[-1]))
+
+    @classmethod
+    def from_rows(cls, ranges, row_ptr_local, cols_global, part_size, device=None, group=None):
+        """A shard built from the rank's OWN rows only (graph.synth_graph_shard, or a loader that reads a vertex range):
+        row_ptr_local [n_local+1] offsets from 0, cols_global [E_local] GLOBAL neighbour ids.  No rank ever holds the
+        whole graph; the global edge count is an all-reduce of the local ones (int64: it exceeds 2^31 for
+        ogbn-papers100M-size graphs while every local CSR stays int32)."""
+        self = cls.__new__(cls)
+        device = torch.device(device) if device is not None else row_ptr_local.device
+        e_local = torch.tensor([int(row_ptr_local[-1])], dtype=torch.int64, device=device)
+        if dist.get_world_size(group) > 1:
+            dist.all_reduce(e_local, group=group)
+        self._setup(list(ranges), row_ptr_local.to(device), cols_global.to(device), part_size, device, group,
+                    num_nodes_global=int(ranges[-1]), num_edges_global=int(e_local.item()))
+        return self
+
+    def _setup(self, ranges, rp_local, cols_global, part_size, device, group, num_nodes_global, num_edges_global):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        device = torch.device(device) if device is not None else row_ptr.device
         self.device = device
         self.part_size = int(part_size)
-        self.ranges = ranges if ranges is not None else partition_ranges(row_ptr, self.world, row_weight)
+        self.ranges = ranges
         v0, v1 = self.ranges[self.rank], self.ranges[self.rank + 1]
         self.v0, self.n_local = v0, v1 - v0
-        self.num_nodes_global = row_ptr.numel() - 1
-        e0, e1 = int(row_ptr[v0]), int(row_ptr[v1])
-        self.num_edges_local = e1 - e0
-        self.num_edges_global = int(row_ptr[-1])
-        rp_local = (row_ptr[v0:v1 + 1].to(torch.int64) - e0).to(torch.int32).to(device)
-        cols = col_idx[e0:e1].to(device).to(torch.int64)
+        self.num_nodes_global = int(num_nodes_global)
+        self.num_edges_local = int(rp_local[-1])
+        self.num_edges_global = int(num_edges_global)
+        if self.num_edges_local >= 2 ** 31:
+            raise ValueError("shard holds %d edges; a local CSR is int32 -- use more ranks" % self.num_edges_local)
+        cols = cols_global.to(torch.int64)
         bounds = torch.tensor(self.ranges, dtype=torch.int64, device=device)
         remote = (cols < v0) | (cols >= v1)
         halo = torch.unique(cols[remote])                                   # sorted => grouped by owner
@@ -99,9 +129,10 @@ class ShardedGraph:
         self.halo_ids = halo
         owner = torch.searchsorted(bounds, halo, right=True) - 1
         self.recv_counts = [int(x) for x in torch.bincount(owner, minlength=self.world).cpu()]
-        local_cols = torch.where(remote, self.n_local + torch.searchsorted(halo, cols), cols - v0)
-        self.row_ptr = rp_local.contiguous()
-        self.col_idx = local_cols.to(torch.int32).contiguous()
+        local_cols = torch.where(remote, self.n_local + torch.searchsorted(halo, cols), cols - v0).to(torch.int32)
+        del cols, remote
+        self.row_ptr = rp_local.to(torch.int32).contiguous()
+        self.col_idx = local_cols.contiguous()
         # tell every owner which of ITS rows we need (as row indices local to the owner)
         want = (halo - bounds[owner]).to(torch.int64)
         rc = torch.tensor(self.recv_counts, dtype=torch.int64, device=device)
@@ -183,11 +214,12 @@ class ShardedGraph:
         """Fill the local rows of the next step's feature buffer from x_local [n_local, D] (scaled by the GCN
         degrees when `prescale`): what a layer's producer (the X*W epilogue) does in a real pipeline."""
         from . import _lib
-        dst = self.local(peer.features())
+        dst = self.local(peer.features(dim=x_local.shape[1]))
         if prescale:
             p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
-            _lib.check(_lib.load().gnna_prescale_rows_f32(p(x_local), p(dst), p(self.degrees_ext), self.n_local, x_local.shape[1],
-                                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "prescale")
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().gnna_prescale_rows_f32(p(x_local), p(dst), p(self.degrees_ext), self.n_local, x_local.shape[1],
+                                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "prescale")
         else:
             dst.copy_(x_local)
         return dst
@@ -199,6 +231,7 @@ class ShardedGraph:
         from . import _lib
         assert self._tables_built and getattr(self, "owner_shards", None), "call build_tables() and build_owner_shards() first"
         lib = _lib.load()
+        torch.cuda.set_device(self.device)            # one process drives one GPU; every launch below goes there
         cur = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_comm_stream"):
             self._comm_stream = torch.cuda.Stream(self.device, priority=-1)
@@ -241,13 +274,14 @@ class ShardedGraph:
             out = torch.empty(self.n_local, d, dtype=torch.float32, device=self.device)
         lib = _lib.load()
         p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = self.part2node.numel()
-        rc = lib.gnna_aggregate_f32_ex(int(mode), p(x_ext), self.n_ext, p(out), self.n_local,
-                                       p(self.row_ptr), p(self.col_idx),
-                                       p(self.degrees_ext) if mode == 1 else ctypes.c_void_p(0), float(eps),
-                                       p(self.part_ptr), p(self.part2node), d, P,
-                                       self.part_size, int(dim_worker), int(warp_per_block), st)
+        with torch.cuda.device(self.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            rc = lib.gnna_aggregate_f32_ex(int(mode), p(x_ext), self.n_ext, p(out), self.n_local,
+                                           p(self.row_ptr), p(self.col_idx),
+                                           p(self.degrees_ext) if mode == 1 else ctypes.c_void_p(0), float(eps),
+                                           p(self.part_ptr), p(self.part2node), d, P,
+                                           self.part_size, int(dim_worker), int(warp_per_block), st)
         _lib.check(rc, "sharded aggregate")
         if peer is not None and do_exchange:
             peer.ack()
@@ -268,12 +302,17 @@ class PeerHalo:
     parity; use `features(step)` to get the [n_ext, dim] tensor a step works on (fill its first n_local
     rows), then `sg.aggregate(..., peer=True)`.
 
+    `dim` is the WIDEST matrix that will be exchanged; a step may exchange any narrower one (`features(dim=d)` /
+    `stage(d)`): the layers of a model trade matrices of different widths through the same mapped buffers.
+
     Collective constructor (all ranks of the group must call it)."""
 
     def __init__(self, sg, dim):
         from . import _lib
         self.sg, self.dim, self.lib = sg, int(dim), _lib.load()
         self.step = 0
+        self.cur_dim = self.dim
+        self._views = {}
         dev, world, rank, group = sg.device, sg.world, sg.rank, sg.group
         self._own = []
         handles = torch.zeros(3, 64, dtype=torch.uint8)
@@ -288,7 +327,7 @@ class PeerHalo:
                 self._own.append(ptr.value)
                 handles[i] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
         self.buf_ptr, self.ctrl_ptr = ptrs[:2], ptrs[2]
-        self.bufs = [torch.as_tensor(_RawCuda(p, (sg.n_ext, self.dim), "<f4"), device=dev) for p in self.buf_ptr]
+        self.bufs = [self._view(b, self.dim) for b in range(2)]
         # everyone learns everyone's handles, local row counts and per-source receive counts
         gathered = [torch.zeros_like(handles) for _ in range(world)]
         meta = torch.tensor([sg.n_local] + sg.recv_counts, dtype=torch.int64)
@@ -334,31 +373,47 @@ class PeerHalo:
         self.c_peer_buf = [(ctypes.c_void_p * world)(*self.peer_buf[b]) for b in range(2)]
         dist.barrier(group=group)
 
-    def features(self, step=None):
-        """The buffer step `step` (default: the next one) gathers from."""
+    def _view(self, parity, dim):
+        key = (parity, int(dim))
+        if key not in self._views:
+            if dim > self.dim:
+                raise ValueError("PeerHalo was mapped for rows of <= %d floats, asked for %d" % (self.dim, dim))
+            self._views[key] = torch.as_tensor(_RawCuda(self.buf_ptr[parity], (self.sg.n_ext, int(dim)), "<f4"), device=self.sg.device)
+        return self._views[key]
+
+    def features(self, step=None, dim=None):
+        """The [n_ext, dim] buffer step `step` (default: the next one) gathers from.  Asking for the NEXT step's buffer
+        also fixes the width that step exchanges."""
+        d = self.cur_dim if dim is None else int(dim)
+        if step is None:
+            self.cur_dim = d
         s = self.step + 1 if step is None else step
-        return self.bufs[s & 1]
+        return self._view(s & 1, d)
+
+    stage = lambda self, dim: self.features(None, dim)   # noqa: E731  (reads better at the call sites of the layers)
 
     def begin_step(self):
         """First call of a step, on the compute (current) stream: advances the step counter on the device.
         Returns the step's feature buffer."""
         from . import _lib
         self.step += 1
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(self.lib.gnna_halo_begin_step(ctypes.c_void_p(self.ctrl_ptr), st), "halo_begin_step")
-        return self.bufs[self.step & 1]
+        with torch.cuda.device(self.sg.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self.lib.gnna_halo_begin_step(ctypes.c_void_p(self.ctrl_ptr), st), "halo_begin_step")
+        return self._view(self.step & 1, self.cur_dim)
 
     def push(self, stream=None):
         """Store my rows into my peers' halo rows (ring order) on `stream`, which must be ordered after begin_step."""
         from . import _lib
         sg = self.sg
         b = self.step & 1
-        st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
-        _lib.check(self.lib.gnna_halo_push_f32(ctypes.c_void_p(self.buf_ptr[b]),
-                                               ctypes.c_void_p(sg.send_idx.data_ptr() if sg.send_idx.numel() else 0),
-                                               self.send_begin, self.c_peer_buf[b], self.c_peer_ctrl, self.c_dst_row0,
-                                               ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.dim, st), "halo_push")
-        return self.bufs[b]
+        with torch.cuda.device(sg.device):
+            st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+            _lib.check(self.lib.gnna_halo_push_f32(ctypes.c_void_p(self.buf_ptr[b]),
+                                                   ctypes.c_void_p(sg.send_idx.data_ptr() if sg.send_idx.numel() else 0),
+                                                   self.send_begin, self.c_peer_buf[b], self.c_peer_ctrl, self.c_dst_row0,
+                                                   ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.cur_dim, st), "halo_push")
+        return self._view(b, self.cur_dim)
 
     def wait(self, peers=None, stream=None):
         """Make `stream` wait until the rows of `peers` (ranks; None = all) for the current step have landed."""
@@ -366,8 +421,9 @@ class PeerHalo:
         mask = 0
         for q in (peers or []):
             mask |= 1 << q
-        st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
-        _lib.check(self.lib.gnna_halo_wait(ctypes.c_void_p(self.ctrl_ptr), self.sg.world, self.sg.rank, mask, st), "halo_wait")
+        with torch.cuda.device(self.sg.device):
+            st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+            _lib.check(self.lib.gnna_halo_wait(ctypes.c_void_p(self.ctrl_ptr), self.sg.world, self.sg.rank, mask, st), "halo_wait")
 
     def exchange(self):
         """Push my rows into my peers' halo rows for the next step and wait for theirs (on the current stream)."""
@@ -379,19 +435,34 @@ class PeerHalo:
     def ack(self):
         """After the aggregation of the current step: producers may overwrite this parity again."""
         from . import _lib
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(self.lib.gnna_halo_ack(self.c_peer_ctrl, ctypes.c_void_p(self.ctrl_ptr), self.sg.world, self.sg.rank, st), "halo_ack")
+        with torch.cuda.device(self.sg.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self.lib.gnna_halo_ack(self.c_peer_ctrl, ctypes.c_void_p(self.ctrl_ptr), self.sg.world, self.sg.rank, st), "halo_ack")
+
+    def error_word(self):
+        """The control block's error word as a 1-element device tensor (no synchronisation): 0 = fine, 1 = a producer
+        here gave up waiting for a peer's acknowledgement, 2 = a flag wait here timed out, 3 = a PRODUCER could not
+        deliver this rank's halo rows (they are stale).  Read it together with something the caller synchronises on
+        anyway (the loss of an epoch)."""
+        return torch.as_tensor(_RawCuda(self.ctrl_ptr + 48 * 4, (1,), "<i4"), device=self.sg.device)
 
     def error(self):
-        """Non-zero if a bounded wait inside a kernel timed out (1: ack wait, 2: flag wait). Synchronises."""
+        """error_word() on the host.  Synchronises."""
         torch.cuda.synchronize(self.sg.device)
-        ctrl = torch.as_tensor(_RawCuda(self.ctrl_ptr, (64,), "<i4"), device=self.sg.device)
-        return int(ctrl[48].item())
+        return int(self.error_word().item())
+
+    def check(self):
+        """Raise if any bounded wait of the exchange timed out since the buffers were mapped.  Synchronises."""
+        e = self.error()
+        if e:
+            raise RuntimeError("halo exchange failed on rank %d (error word %d: %s)" % (
+                self.sg.rank, e, {1: "no acknowledgement from a peer", 2: "a peer's rows never arrived",
+                                  3: "a peer could not deliver this rank's halo rows"}.get(e, "?")))
 
     def close(self):
         torch.cuda.synchronize(self.sg.device)
         dist.barrier(group=self.sg.group)
-        self.bufs = []
+        self.bufs, self._views = [], {}
         with torch.cuda.device(self.sg.device):
             for p in self._opened:
                 self.lib.gnna_ipc_close(ctypes.c_void_p(p))

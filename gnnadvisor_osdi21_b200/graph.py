@@ -21,6 +21,12 @@ def csr_from_edges(src, dst, num_nodes):
     src = torch.as_tensor(src).to(torch.int64).reshape(-1)
     dst = torch.as_tensor(dst).to(torch.int64).reshape(-1)
     num_nodes = int(num_nodes)
+    if src.numel() != dst.numel():
+        raise ValueError("src and dst differ in length (%d vs %d)" % (src.numel(), dst.numel()))
+    if src.numel() and (int(torch.minimum(src.min(), dst.min())) < 0 or int(torch.maximum(src.max(), dst.max())) >= num_nodes):
+        # scipy's coo_matrix raises here too ("row index exceeds matrix dimensions"); without the check an id
+        # >= num_nodes would alias into another row of the src*N+dst key
+        raise ValueError("edge endpoint outside [0, %d)" % num_nodes)
     key = torch.unique(src * num_nodes + dst)           # sorted by (src, dst), duplicates merged
     rows = torch.div(key, num_nodes, rounding_mode="floor")
     cols = (key - rows * num_nodes).to(torch.int32)
@@ -40,61 +46,132 @@ def degrees_from_row_ptr_host(row_ptr):
 
 # ------------------------------------------------------------------------------------------ synthetic graphs
 RMAT_DEFAULT = (0.48, 0.14, 0.14, 0.24)    # (a+b)^18 * 115e6 ~ 2e4: hub degree like Reddit's 21 657
+# (SURVEY.md 8d suggests (0.57, 0.19, 0.19, 0.05); that puts 10x Reddit's hub degree on node 0, so the look-alikes use
+# the flatter set above.  bench.py prints the parameters in config.)
+
+# The pair stream is COUNTER-BASED: pair k of a graph is a pure function of (seed, k) -- splitmix64 over int64 tensors,
+# wrapping arithmetic -- so the same graph comes out on the CPU and on any GPU, any slice [k0, k1) of the stream can be
+# generated on its own, and N ranks can each generate exactly the rows they own without anyone holding the whole graph.
+_M64 = (1 << 64) - 1
 
 
-def _rmat_pairs(num_nodes, count, params, gen, device):
-    a, b, c, _ = params
-    bits = max(1, math.ceil(math.log2(max(num_nodes, 2))))
-    src = torch.zeros(count, dtype=torch.int64, device=device)
-    dst = torch.zeros(count, dtype=torch.int64, device=device)
-    for _ in range(bits):
-        r = torch.rand(count, generator=gen, device=device)
-        sbit = (r >= a + b).to(torch.int64)
-        dbit = (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
-        src = src * 2 + sbit
-        dst = dst * 2 + dbit
-    keep = (src < num_nodes) & (dst < num_nodes) & (src != dst)
+def _s64(c):
+    c &= _M64
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+_C1, _C2, _GOLD = _s64(0xBF58476D1CE4E5B9), _s64(0x94D049BB133111EB), 0x9E3779B97F4A7C15
+
+
+def _mix64(x):
+    """splitmix64 finaliser on an int64 tensor (logical shifts emulated by masking the sign extension)."""
+    x = x ^ ((x >> 30) & 0x3FFFFFFFF)
+    x = x * _C1
+    x = x ^ ((x >> 27) & 0x1FFFFFFFFF)
+    x = x * _C2
+    return x ^ ((x >> 31) & 0x1FFFFFFFF)
+
+
+def stream_pairs(num_nodes, start, count, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT):
+    """Pairs [start, start+count) of the directed pair stream of graph (num_nodes, kind, seed): (src, dst) int64
+    tensors with self loops and out-of-range ids already dropped (so fewer than `count` come back)."""
+    N = int(num_nodes)
+    idx = torch.arange(int(start), int(start) + int(count), dtype=torch.int64, device=device)
+    base = _mix64(idx ^ _s64(int(seed) * _GOLD + 0x1234567))
+    if kind == "uniform":
+        h = _mix64(base + _s64(_GOLD))
+        src = (((h >> 32) & 0xFFFFFFFF) * N) >> 32
+        dst = ((h & 0xFFFFFFFF) * N) >> 32
+    else:
+        a, b, c, _ = rmat
+        t_a, t_ab, t_abc = int(a * 2 ** 32), int((a + b) * 2 ** 32), int((a + b + c) * 2 ** 32)
+        bits = max(1, math.ceil(math.log2(max(N, 2))))
+        src = torch.zeros_like(idx)
+        dst = torch.zeros_like(idx)
+        for lvl in range(bits):
+            if lvl % 2 == 0:
+                h = _mix64(base + _s64((lvl // 2 + 1) * _GOLD))
+                u = (h >> 32) & 0xFFFFFFFF
+            else:
+                u = h & 0xFFFFFFFF
+            src = src * 2 + (u >= t_ab).to(torch.int64)
+            dst = dst * 2 + (((u >= t_a) & (u < t_ab)) | (u >= t_abc)).to(torch.int64)
+    keep = (src < N) & (dst < N) & (src != dst)
     return src[keep], dst[keep]
 
 
-def _uniform_pairs(num_nodes, count, gen, device):
-    src = torch.randint(0, num_nodes, (count,), generator=gen, device=device)
-    dst = torch.randint(0, num_nodes, (count,), generator=gen, device=device)
-    keep = src != dst
-    return src[keep], dst[keep]
-
-
-def synth_graph(num_nodes, num_edges, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT):
+def synth_graph(num_nodes, num_edges, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT, exact=True):
     """Symmetric graph with exactly 2*floor(num_edges/2) directed edges (when that many distinct
     pairs exist), no self loops, last node non-isolated.  Returns (row_ptr, col_idx)
     int32 on `device`.  kind: "rmat" (skewed, Reddit/products/papers look-alikes) or "uniform"
-    (Cora/citeseer look-alikes).  Deterministic for a given (seed, device type)."""
+    (Cora/citeseer look-alikes).  Deterministic for a given seed on every device.
+    exact=False: the first floor(num_edges/2) pairs of the stream, duplicates merged ("as generated", what
+    synth_graph_shard produces piecewise)."""
     device = torch.device(device)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(int(seed))
     want_pairs = max(1, int(num_edges) // 2)
     N = int(num_nodes)
     und = torch.empty(0, dtype=torch.int64, device=device)      # undirected keys lo*N+hi, lo<hi
-    draw = int(want_pairs * 1.1) + 16
+    pos, draw = 0, (int(want_pairs * 1.1) + 16 if exact else want_pairs)
     for _ in range(64):
-        s, d = _rmat_pairs(N, draw, rmat, gen, device) if kind == "rmat" else _uniform_pairs(N, draw, gen, device)
+        s, d = stream_pairs(N, pos, draw, kind, seed, device, rmat)
+        pos += draw
         lo, hi = torch.minimum(s, d), torch.maximum(s, d)
         und = torch.unique(torch.cat([und, lo * N + hi]))
-        if und.numel() >= want_pairs:
+        if not exact or und.numel() >= want_pairs:
             break
         draw = int((want_pairs - und.numel()) * 1.5) + 16
-    if und.numel() > want_pairs:
-        perm = torch.randperm(und.numel(), generator=gen, device=device)[:want_pairs]
-        und = und[perm]
+    if und.numel() > want_pairs:       # keep the pairs with the smallest hashes: a fixed, device-independent subset
+        order = torch.sort(_mix64(und + _s64(int(seed) * _GOLD)))[1][:want_pairs]
+        und = und[order]
     lo = torch.div(und, N, rounding_mode="floor")
     hi = und - lo * N
     # make sure the last node has a neighbour (its partPtr terminal is then written by the reference too)
-    if not bool(((lo == N - 1) | (hi == N - 1)).any()) and N > 1:
+    if exact and not bool(((lo == N - 1) | (hi == N - 1)).any()) and N > 1:
         lo = torch.cat([lo, torch.tensor([0], device=device)])
         hi = torch.cat([hi, torch.tensor([N - 1], device=device)])
     src = torch.cat([lo, hi])
     dst = torch.cat([hi, lo])
     return csr_from_edges(src, dst, N)
+
+
+def stream_degree_estimate(num_nodes, num_pairs, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT,
+                           chunk=1 << 25, every=1):
+    """Row degrees of the symmetrised pair stream BEFORE duplicate merging (int64 [N]); what the sharded generator cuts
+    its vertex ranges from.  every=k looks at one chunk in k (a k-fold cheaper estimate, scaled back up)."""
+    N = int(num_nodes)
+    deg = torch.zeros(N, dtype=torch.int64, device=device)
+    one = None
+    for ci, pos in enumerate(range(0, int(num_pairs), chunk)):
+        if ci % every:
+            continue
+        s, d = stream_pairs(N, pos, min(chunk, int(num_pairs) - pos), kind, seed, device, rmat)
+        if one is None or one.numel() < s.numel():
+            one = torch.ones(s.numel(), dtype=torch.int64, device=device)
+        deg.index_add_(0, s, one[:s.numel()])
+        deg.index_add_(0, d, one[:s.numel()])
+    return deg * every
+
+
+def synth_graph_shard(num_nodes, num_edges, v0, v1, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT,
+                      chunk=1 << 25):
+    """Rows [v0, v1) of synth_graph(num_nodes, num_edges, exact=False) without ever holding the rest:
+    every rank walks the same counter-based pair stream and keeps the directed edges whose SOURCE it owns.
+    Returns (row_ptr int64 [v1-v0+1] local offsets, col int32 [E_local] GLOBAL ids), duplicates merged, sorted."""
+    N, v0, v1 = int(num_nodes), int(v0), int(v1)
+    want_pairs = max(1, int(num_edges) // 2)
+    keys = []
+    for pos in range(0, want_pairs, chunk):
+        s, d = stream_pairs(N, pos, min(chunk, want_pairs - pos), kind, seed, device, rmat)
+        for a, b in ((s, d), (d, s)):
+            m = (a >= v0) & (a < v1)
+            keys.append((a[m] - v0) * N + b[m])
+    key = torch.unique(torch.cat(keys)) if keys else torch.empty(0, dtype=torch.int64, device=device)
+    del keys
+    rows = torch.div(key, N, rounding_mode="floor")
+    cols = (key - rows * N).to(torch.int32)
+    row_ptr = torch.zeros(v1 - v0 + 1, dtype=torch.int64, device=key.device)
+    row_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=v1 - v0), 0)
+    return row_ptr, cols
 
 
 # sizes of the BASELINE.json configurations (public dataset statistics, SURVEY.md 8)
@@ -165,8 +242,7 @@ class GraphDataset(torch.nn.Module):
         self.degrees = degrees_from_row_ptr_host(self.row_pointers).to(self.device)
 
     def rabbit_reorder(self):
-        """Renumber the vertices for locality and rebuild the CSR (dataset.py:138-175).  Unlike the
-        reference the degree vector is refreshed too."""
+        """Renumber the vertices for locality and rebuild the CSR and the degree vector (dataset.py:138-175)."""
         if not self.reorder_flag:
             return
         from . import reorder as _reorder
@@ -177,12 +253,27 @@ class GraphDataset(torch.nn.Module):
         self._refresh_degrees()
 
 
-custom_dataset = GraphDataset
+class custom_dataset(GraphDataset):
+    """The reference's constructor (dataset.py:24: custom_dataset(path, dim, num_class, load_from_txt=True, verbose=False))
+    and its train/val/test masks (:44-53: the first 100 % / 30 % / 10 % of the nodes)."""
+
+    def __init__(self, path, dim, num_class, load_from_txt=True, verbose=False, device="cuda"):
+        if not load_from_txt and not str(path).endswith(".npz"):
+            raise ValueError("graph file must be a .npz file")          # dataset.py:83-84
+        super().__init__(dim, num_class, edges=load_edge_file(path, text=bool(load_from_txt)), device=device, verbose=verbose)
+        self.load_from_txt = load_from_txt
+        n = self.num_nodes
+        idx = torch.arange(n, device=self.device)
+        self.train_mask = idx < int(n * 1)
+        self.val_mask = idx < int(n * 0.3)
+        self.test_mask = idx < int(n * 0.1)
 
 
-def load_edge_file(path):
-    """(src, dst, num_nodes) from a reference-format .npz or a text edge list (dataset.py:58-94)."""
-    if path.endswith(".npz"):
+
+def load_edge_file(path, text=None):
+    """(src, dst, num_nodes) from a reference-format .npz or a text edge list (dataset.py:58-94).
+    text: None = by extension, True/False = the reference's load_from_txt switch."""
+    if (text is None and path.endswith(".npz")) or text is False:
         obj = np.load(path)
         return obj["src_li"], obj["dst_li"], int(obj["num_nodes"])
     src, dst = [], []

@@ -126,7 +126,8 @@ def main(argv=None):
     info.column_index = info.column_index.to(device)
     info.partPtr = part_ptr.int().to(device)                                     # :109-110
     info.part2Node = part2node.int().to(device)
-    info.degrees = dataset.degrees.to(device)     # refreshed after a reorder (the reference keeps the stale ones, F11)
+    info.degrees = dataset.degrees.to(device)     # dataset.degrees is regenerated by rabbit_reorder (dataset.py:170-172); the reference's inputInfo
+    # keeps the copy it captured BEFORE the reorder (GNNA_main.py:75) -- here the fresh one is used
 
     if args.verify_spmm == "True":
         return 0 if verify_spmm(info, dataset, args.hidden) else 1

@@ -373,26 +373,32 @@ def _build_part_host(partSize, indptr, compat):
     return pp, pn
 
 
-def build_part(partSize, indptr):
+def build_part(partSize, indptr, compat=None):
     """Neighbour-group table.  Reference: build_part, GNNAdvisor.cpp:210-251.
 
-    CPU int32 indptr (what GNNA_main.py:102 passes): returns what the reference returns, bit for bit --
-    two float32 CPU tensors, including the reference's terminal-entry rule when the last node is
-    isolated -- as long as every offset is exactly representable in float32
-    (< 2^24).  Beyond that the reference's float table is silently corrupt (F5); we return the exact
-    int32 table instead (the caller's `.int()` is then a no-op) and warn once.
-    Set GNNA_BUILD_PART=exact to always get the exact int32 table (terminal = indptr[-1]).
+    CPU int32 indptr (what GNNA_main.py:102 passes): two float32 CPU tensors like the reference's (the caller's `.int()`
+    recovers the table), as long as every offset is exactly representable in float32 (< 2^24).  Beyond that the reference's
+    float table is silently corrupt; the exact int32 table is returned instead (`.int()` is then a no-op) with
+    a warning.
+
+    The terminal entry is ALWAYS indptr[-1].  The reference leaves it 0 when the last node is isolated (F6), which makes
+    every kernel drop the last non-isolated node's final group; a table consumed by this runtime must not do that.
+    compat=True (or GNNA_BUILD_PART=compat) reproduces the reference's table bit for bit, F6 included -- what the golden
+    tests pin.  GNNA_BUILD_PART=exact always returns the int32 table.
     CUDA indptr: the table is built on the GPU, exact, returned as int32 CUDA tensors."""
     if indptr.is_cuda:
         return build_part_exact(partSize, indptr)
-    if os.environ.get("GNNA_BUILD_PART", "compat") == "exact":
+    env = os.environ.get("GNNA_BUILD_PART", "")
+    if compat is None:
+        compat = env == "compat"
+    if env == "exact" and not compat:
         return build_part_exact(partSize, indptr)
     n_edges = int(indptr[-1]) if indptr.numel() > 0 else 0
     if max(n_edges, indptr.numel()) >= _F32_EXACT_LIMIT:
         warnings.warn("build_part: offsets exceed 2^24; returning exact int32 tables "
                       "(the reference's float32 tables are rounded here)", stacklevel=2)
         return build_part_exact(partSize, indptr)
-    pp, pn = _build_part_host(partSize, indptr, compat=True)
+    pp, pn = _build_part_host(partSize, indptr, compat=bool(compat))
     return [pp.float(), pn.float()]
 
 

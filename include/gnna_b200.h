@@ -122,6 +122,12 @@ GNNA_API int gnna_aggregate_part_f32_ex(int mode, int accumulate, const float *X
  * so a producer can hand pre-scaled rows to gnna_aggregate_part_f32_ex(mode 3) / the halo push.          */
 GNNA_API int gnna_prescale_rows_f32(const float *X, float *Xs, const float *degrees, int64_t num_rows, int dim, void *stream);
 
+/* Row-major C[m,n] = op(A) * op(B), fp32 (cuBLAS SGEMM, TF32 off): the library call the reference makes through
+ * torch::mm (GNNAdvisor_kernel.cu:280,472,473,605,710,711), for callers that compose a layer from its parts --
+ * the sharded layers run product, halo exchange and aggregation as separate steps.                        */
+GNNA_API int gnna_sgemm_f32(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
+                            const float *A, const float *B, float *C, void *stream);
+
 /* bf16-storage variant: neighbour rows are gathered as bf16 (half the gather bytes), summed in
  * fp32 and written as fp32.  An extension: the reference is fp32-only.
  * mode: 0 = SAG, 1 = GCN (degrees, per-edge weights), 2 = GIN (eps), 3 = GCN on features the caller

@@ -62,15 +62,19 @@ def bp_golden():
 
 
 def test_build_part_matches_reference_golden(bp_golden):
-    """ops.build_part on a CPU IntTensor returns the reference's float32 tensors verbatim."""
+    """ops.build_part(compat=True) on a CPU IntTensor returns the reference's float32 tensors verbatim (F6 included);
+    the default differs from it only in the terminal entry of a graph whose last node is isolated."""
     names = sorted({k.split("/")[1] for k in bp_golden.files if k.startswith("partPtr/")})
     for name in names:
         indptr = torch.from_numpy(bp_golden["indptr/" + name])
         for ps in PART_SIZES:
-            pp, pn = ops.build_part(ps, indptr)
+            pp, pn = ops.build_part(ps, indptr, compat=True)
             assert pp.dtype == torch.float32 and pn.dtype == torch.float32 and not pp.is_cuda
             assert np.array_equal(pp.numpy(), bp_golden["partPtr/%s/%d" % (name, ps)]), (name, ps)
             assert np.array_equal(pn.numpy(), bp_golden["part2Node/%s/%d" % (name, ps)]), (name, ps)
+            dpp, dpn = ops.build_part(ps, indptr)                      # default: same table, terminal always indptr[-1]
+            assert dpp.dtype == torch.float32 and np.array_equal(dpn.numpy(), pn.numpy())
+            assert np.array_equal(dpp.numpy()[:-1], pp.numpy()[:-1]) and (dpp.numel() == 1 or int(dpp[-1]) == int(indptr[-1]))
             epp, epn = ops.build_part_exact(ps, indptr)
             opp, opn = oracle.build_part(ps, indptr.numpy(), exact=True)
             assert epp.dtype == torch.int32 and np.array_equal(epp.numpy(), opp) and np.array_equal(epn.numpy(), opn)

@@ -1,0 +1,101 @@
+"""CSR construction and the dataset object against what the reference does (GNNAdvisor/dataset.py:55-122):
+scipy coo_matrix(...).tocsr() on the raw edge list (duplicates merged, columns sorted), degrees = sqrt(max(deg, 1)),
+the reference's constructor signature and masks; plus the device-independent, shardable graph generator."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from gnnadvisor_osdi21_b200 import graph
+
+
+def _scipy_csr(src, dst, n):
+    csr = sp.coo_matrix((np.ones(len(src)), (src, dst)), shape=(n, n)).tocsr()     # dataset.py:110-111
+    csr.sort_indices()
+    return csr.indptr.astype(np.int32), csr.indices.astype(np.int32)
+
+
+@pytest.mark.parametrize("n,e,seed", [(50, 400, 0), (1000, 30000, 1), (7, 0, 2), (300, 5000, 3)])
+def test_csr_from_edges_equals_scipy_coo_to_csr(n, e, seed):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n, e)
+    dst = rng.integers(0, max(n // 3, 1), e)                  # a third of the id range: many duplicate edges
+    if e:
+        src[: e // 4] = src[e // 4: 2 * (e // 4)]             # exact duplicates, self loops stay in
+        dst[: e // 4] = dst[e // 4: 2 * (e // 4)]
+    rp, ci = graph.csr_from_edges(src, dst, n)
+    erp, eci = _scipy_csr(src, dst, n)
+    assert rp.dtype == torch.int32 and ci.dtype == torch.int32
+    assert np.array_equal(rp.numpy(), erp) and np.array_equal(ci.numpy(), eci)
+    # degrees: sqrt(max(deg, 1)) in float32 (dataset.py:11-18,121-122)
+    deg = graph.degrees_from_row_ptr_host(rp).numpy()
+    d = np.diff(erp).astype(np.float32)
+    assert np.array_equal(deg, np.sqrt(np.maximum(d, 1).astype(np.float32)))
+
+
+def test_csr_from_edges_rejects_out_of_range_ids():
+    with pytest.raises(ValueError, match="outside"):
+        graph.csr_from_edges([0, 5], [1, 2], 5)               # scipy raises as well
+    with pytest.raises(ValueError, match="outside"):
+        graph.csr_from_edges([0, 1], [-1, 2], 5)
+    with pytest.raises(ValueError):
+        sp.coo_matrix((np.ones(2), ([0, 5], [1, 2])), shape=(5, 5))
+
+
+def test_custom_dataset_has_the_reference_constructor(tmp_path):
+    rng = np.random.default_rng(4)
+    src, dst = rng.integers(0, 40, 300), rng.integers(0, 40, 300)
+    npz = str(tmp_path / "g.npz")
+    graph.save_npz(npz, src, dst, 40)
+    ds = graph.custom_dataset(npz, 16, 10, load_from_txt=False, verbose=False, device="cpu")    # dataset.py:24
+    erp, eci = _scipy_csr(src, dst, 40)
+    assert np.array_equal(ds.row_pointers.numpy(), erp) and np.array_equal(ds.column_index.numpy(), eci)
+    assert ds.num_nodes == 40 and ds.num_edges == 300 and ds.num_features == 16 and ds.num_classes == 10
+    assert ds.x.shape == (40, 16) and ds.y.dtype == torch.long and bool((ds.y == 1).all())
+    assert abs(ds.avg_degree - 300 / 40) < 1e-12 and abs(ds.avg_edgeSpan - np.mean(np.abs(src - dst))) < 1e-9
+    assert int(ds.train_mask.sum()) == 40 and int(ds.val_mask.sum()) == 12 and int(ds.test_mask.sum()) == 4   # :44-53
+    txt = str(tmp_path / "g.txt")
+    with open(txt, "w") as f:
+        for a, b in zip(src, dst):
+            f.write("%d %d\n" % (a, b))
+    dt = graph.custom_dataset(txt, 16, 10, load_from_txt=True, device="cpu")
+    assert dt.num_nodes == int(max(src.max(), dst.max())) + 1
+    assert np.array_equal(dt.column_index.numpy(), _scipy_csr(src, dst, dt.num_nodes)[1])
+    with pytest.raises(ValueError, match=".npz"):
+        graph.custom_dataset(txt, 16, 10, load_from_txt=False, device="cpu")
+
+
+def test_splitmix64_matches_the_published_algorithm():
+    M = (1 << 64) - 1
+
+    def ref(x):
+        x &= M
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
+        return x ^ (x >> 31)
+    vals = [0, 1, 12345, (1 << 63) - 1, -1, -(1 << 63), 0x9E3779B97F4A7C15 - (1 << 64)]
+    got = graph._mix64(torch.tensor(vals, dtype=torch.int64))
+    assert [int(g) & M for g in got] == [ref(v) for v in vals]
+
+
+@pytest.mark.parametrize("kind", ["rmat", "uniform"])
+def test_shards_of_the_pair_stream_tile_the_whole_graph(kind):
+    n, e, seed = 5000, 160000, 9
+    rp, ci = graph.synth_graph(n, e, kind=kind, seed=seed, exact=False)
+    # symmetric, no self loops, sorted unique columns
+    A = sp.csr_matrix((np.ones(ci.numel()), ci.numpy(), rp.numpy()), shape=(n, n))
+    assert (A != A.T).nnz == 0 and A.diagonal().sum() == 0
+    est = graph.stream_degree_estimate(n, e // 2, kind=kind, seed=seed, chunk=30011)
+    assert int(est.sum()) >= int(rp[-1]) and bool((est >= (rp[1:] - rp[:-1]).long()).all())   # pre-dedup counts bound the rows
+    cuts = [0, 1, 1200, 3100, 4999, 5000]
+    for v0, v1 in zip(cuts[:-1], cuts[1:]):
+        r, c = graph.synth_graph_shard(n, e, v0, v1, kind=kind, seed=seed, chunk=30011)      # chunking must not matter
+        assert torch.equal(r, rp[v0:v1 + 1].long() - int(rp[v0]))
+        assert torch.equal(c, ci[int(rp[v0]):int(rp[v1])])
+
+
+def test_exact_lookalike_sizes_and_last_node():
+    rp, ci = graph.synth_graph(2708, 10556, kind="uniform", seed=20211)
+    assert int(rp[-1]) == 10556 and int(rp[-1] - rp[-2]) > 0
+    rp2, ci2 = graph.synth_graph(2708, 10556, kind="uniform", seed=20211)
+    assert torch.equal(rp, rp2) and torch.equal(ci, ci2)
