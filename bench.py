@@ -65,6 +65,75 @@ def peak_gbs():
     return PEAK_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+_L2_PEAK = {}
+
+
+def l2_peak_gbs(device=None):
+    """L2 -> SM read bandwidth of THIS box, measured live with the library's probe kernel (csrc/probe.cu): a 32 MB buffer
+    (fits the 126 MB L2, 100x an SM's L1) read 40 times with the gather's own 128-bit load instruction, timed with CUDA events after one warming launch.
+    seq = coalesced stream (the highest rate the path delivers: the roof), rows = randomly ordered 256-byte rows (the D=64
+    fp32 gather's access pattern).  Cached per process."""
+    import ctypes
+    from gnnadvisor_osdi21_b200 import _lib
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device.index in _L2_PEAK:
+        return _L2_PEAK[device.index]
+    lib = _lib.load()
+    nbytes, passes = 32 << 20, 40
+    with torch.cuda.device(device):
+        buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
+        sink = torch.zeros(1, dtype=torch.int32, device=device)
+        res = {"buffer_MB": nbytes >> 20, "passes": passes, "l2_size_MB": torch.cuda.get_device_properties(device).L2_cache_size / 2 ** 20}
+        for name, mode in (("seq", 0), ("rows256", 1)):
+            def run():
+                _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), nbytes, passes, mode, 2, ctypes.c_void_p(sink.data_ptr()),
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2 probe")
+            best = min(timed(run, 1, 1) for _ in range(5))
+            res[name + "_GBs"] = nbytes * passes / (best * 1e-3) / 1e9
+    _L2_PEAK[device.index] = res
+    return res
+
+
+def roofline_of(B, kernel_ms, feature_bytes, kernel, note="", traffic=None, traffic_source=None, **extra):
+    """The roofline object of one aggregation launch.  B = algorithmic bytes of the launch (alg_bytes), kernel_ms = its
+    live CUDA-event time.  The roof depends on where the gathered matrix lives: when it fits in L2 (feature_bytes < 60 % of
+    the L2) every neighbour-row read is an L2 hit and the bound is the L2 -> SM path, whose peak is measured on this box
+    (l2_peak_gbs); otherwise the bound is HBM and the peak is MEASURED_PEAKS.json's copy bandwidth.  The HBM line is always
+    carried too (`hbm`): for the L2-resident case its fraction exceeds 1 -- it is a ratio of algorithmic bytes to a DRAM
+    peak the kernel does not use -- and `traffic` (ncu dram bytes of a capture of this kernel, when one is committed under
+    profiles/) says how much DRAM traffic there really is."""
+    hbm_peak, hbm_src = peak_gbs()
+    achieved = B / (kernel_ms * 1e-3) / 1e9
+    l2 = l2_peak_gbs()
+    l2_resident = feature_bytes < 0.6 * l2["l2_size_MB"] * 2 ** 20
+    r = {"bound": "l2" if l2_resident else "hbm", "achieved": achieved,
+         "peak": l2["seq_GBs"] if l2_resident else hbm_peak, "unit": "GB/s",
+         "frac": achieved / (l2["seq_GBs"] if l2_resident else hbm_peak),
+         "traffic": traffic, "traffic_source": traffic_source, "kernel": kernel, "alg_bytes_per_launch": B, "kernel_ms": kernel_ms,
+         "peak_source": ("L2 -> SM read bandwidth measured live on this GPU (gnna_probe_l2_read: 32 MB buffer, ld.global.nc.v4, "
+                         "coalesced, every byte once per pass)" if l2_resident else hbm_src),
+         "gathered_matrix_MB": feature_bytes / 1e6,
+         "l2_probe": l2,
+         "frac_of_random_row_l2_rate": achieved / l2["rows256_GBs"],
+         "hbm": {"achieved": achieved, "peak": hbm_peak, "frac": achieved / hbm_peak, "peak_source": hbm_src,
+                 "dram_GBs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None,
+                 "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None},
+         "note": note}
+    r.update(extra)
+    return r
+
+
+def committed_traffic(key):
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of a kernel capture committed under profiles/
+    (profiles/dram_traffic.json: value + the capture file it was read from), or (None, None)."""
+    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        prof = json.load(open(tp))
+        return prof.get(key), prof.get(key + "_source")
+    except Exception:   # noqa: BLE001
+        return None, None
+
+
 def alg_bytes(E, N, D, P, sx=4, sy=4, gcn=False, prescale=False):
     """E*(D*sx + 4 [+4 per-edge degree gather, exact GCN mode only]) + N*(D*sy + 8) + part table
     (2P+1)*4 [+ 2*N*D*sx for the pre-scale pass of the default GCN mode]."""
@@ -323,30 +392,16 @@ def run_single(args):
     peak, peak_src = peak_gbs()
     B = alg_bytes(E, N, D, P)                      # one launch of the gather (the pre-scale pass is another kernel)
     B_step = alg_bytes(E, N, D, P, prescale=True)
-    achieved = B / (kernel_ms * 1e-3) / 1e9
-    traffic, l2_bytes, l2_port = None, None, None
-    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tp) and args.scale == 1.0:
-        try:
-            prof = json.load(open(tp))
-            traffic = prof.get("%s_D%d_f32" % (args.workload, D))
-            l2_bytes = prof.get("%s_D%d_f32_l2_to_sm_bytes" % (args.workload, D))
-            l2_port = prof.get("%s_D%d_f32_l2_port_pct" % (args.workload, D))
-        except Exception:   # noqa: BLE001
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "gnna::aggregate_kernel<float,4,16,1,false> (+ prescale_rows_kernel<4>, 0.4% of the bytes)",
-                "alg_bytes_per_launch": B, "peak_source": peak_src,
-                "kernel_ms": kernel_ms, "kernel_launches_per_call": int(kernel_launches), "kernel_share_of_step": kernel_ms / ms,
-                "achieved_whole_step": B_step / (ms * 1e-3) / 1e9,
-                "dram_GBs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None,
-                "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                "l2_to_sm_GBs": (l2_bytes / (kernel_ms * 1e-3) / 1e9) if l2_bytes else None,
-                "l2_port_pct_of_peak_ncu": l2_port,
-                "note": "achieved = alg_bytes_per_launch / kernel_ms, kernel_ms = the aggregate kernel alone timed live with CUDA events "
-                        "(one launch per call); the step (ms_per_step) = cudaMemsetAsync(out) + prescale_rows + that kernel; features (%.0f MB) fit in L2, so "
-                        "achieved may exceed the HBM copy peak -- see traffic (ncu dram bytes per launch); the binding unit is then the "
-                        "L2 -> SM port (l2_port_pct_of_peak_ncu, from the committed ncu capture of this kernel)" % (N * D * 4 / 1e6)}
+    traffic, traffic_src = committed_traffic("%s_D%d_f32" % (args.workload, D)) if args.scale == 1.0 else (None, None)
+    roofline = roofline_of(
+        B, kernel_ms, N * D * 4, traffic=traffic, traffic_source=traffic_src,
+        kernel="gnna::aggregate_kernel<float,4,16,1,false> (+ prescale_rows_kernel<4>, 0.4% of the bytes)",
+        note="achieved = alg_bytes_per_launch / kernel_ms, kernel_ms = the aggregate kernel alone timed live with CUDA events (one launch "
+             "per call); the step (ms_per_step) = cudaMemsetAsync(out) + prescale_rows + that kernel.  bound = l2 when the gathered "
+             "matrix is L2-resident: peak is then the L2 -> SM read bandwidth measured on this GPU in this run, and `hbm` keeps the "
+             "algorithmic-bytes-over-HBM-peak ratio (> 1 is possible there) next to the DRAM bytes ncu saw",
+        kernel_launches_per_call=int(kernel_launches), kernel_share_of_step=kernel_ms / ms,
+        achieved_whole_step=B_step / (ms * 1e-3) / 1e9)
 
     # ---- end to end through the public API with host buffers
     # the aggregation-only entry of the C ABI (gnna_gcn_aggregate_f32, the kernel behind
@@ -410,7 +465,7 @@ def run_single(args):
             bms = timed(f, max(3, args.steps // 4), 3) / max(3, args.steps // 4)
             Bb = alg_bytes(E, N, D, P, sx=2)
             extras["bf16_gather"] = {"ms": bms, "edge_dim_per_s": E * D / (bms * 1e-3), "achieved_GBs": Bb / (bms * 1e-3) / 1e9,
-                                     "frac": Bb / (bms * 1e-3) / 1e9 / peak}
+                                     "frac_of_hbm_peak": Bb / (bms * 1e-3) / 1e9 / peak}
         except Exception as e:   # noqa: BLE001
             extras["bf16_gather"] = {"error": str(e)}
         # 2-layer GCN epoch (forward + backward + Adam), mirrors GNNA_main.py:142-202
@@ -428,6 +483,18 @@ def run_single(args):
             extras["ref_gpu"] = ref_gpu(args, X, rp, ci, deg, pp, pn, step, ms)
         except Exception as e:   # noqa: BLE001
             extras["ref_gpu"] = {"error": str(e)}
+        try:
+            extras["ref_gpu"]["epoch_ms"] = ref_gpu_epoch(args, gr, rp, ci, deg, pp, pn, device)
+        except Exception as e:   # noqa: BLE001
+            extras["ref_gpu"]["epoch_ms"] = {"error": str(e)[:300]}
+        # the genuinely HBM-bound case next to the L2-resident headline: ogbn-products look-alike (627 MB of features)
+        if args.workload == "reddit" and args.scale == 1.0:
+            try:
+                del x_dev, o_dev
+                torch.cuda.empty_cache()
+                extras["hbm_bound_leg"] = hbm_bound_leg(args, device)
+            except Exception as e:   # noqa: BLE001
+                extras["hbm_bound_leg"] = {"error": str(e)}
         line["extras"] = extras
         try:
             line["cpu_baseline"] = cpu_pass(args, rp, ci, pp, pn, deg, X, args.cpu_seconds)
@@ -462,6 +529,89 @@ def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, gather_dtype="fp32"):
     return {"ms": timed(train, k, 3) / k, "epochs_timed": k,
             "model": "GCN %d-%d-%d, fwd+bwd+Adam (GNNA_main.py:142-202), gathered rows %s"
                      % (gr["in_dim"], gr["hidden"], gr["classes"], gather_dtype)}
+
+
+def hbm_bound_leg(args, device):
+    """One aggregation launch on the ogbn-products look-alike (2.45 M nodes, 123.7 M edges, D=64 fp32: the gathered matrix
+    is 5x the L2), kernel alone, CUDA-event timed: the roofline line of the HBM-bound regime."""
+    import ctypes
+    from gnnadvisor_osdi21_b200 import _lib, graph, ops
+    lib = _lib.load()
+    gr = graph.lookalike("ogbn-products", device=device)
+    rp, ci = gr["row_ptr"], gr["col_idx"]
+    pp, pn = ops.build_part(args.part_size, rp)
+    deg = ops.degrees_from_row_ptr(rp)
+    N, E, P, D = gr["num_nodes"], ci.numel(), pn.numel(), 64
+    Xs = torch.randn(N, D, device=device, generator=torch.Generator(device=device).manual_seed(20212))
+    acc = torch.zeros_like(Xs)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+
+    def kernel_only():
+        _lib.check(lib.gnna_aggregate_part_f32_ex(3, 1, p(Xs), N, p(acc), N, p(rp), p(ci), p(deg), 0.0, p(pp), p(pn), D, P,
+                                                  args.part_size, args.dim_worker, args.warp_per_block,
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "aggregate (kernel only)")
+    k = max(5, min(args.steps, 30))
+    kernel_ms = timed(kernel_only, k, 3) / k
+    traffic, src = committed_traffic("ogbn-products_D64_f32")
+    r = roofline_of(alg_bytes(E, N, D, P), kernel_ms, N * D * 4, traffic=traffic, traffic_source=src,
+                    kernel="gnna::aggregate_kernel<float,4,16,1,false>",
+                    note="L2 absorbs the hub rows, so DRAM traffic (hbm.dram_GBs, from the committed ncu capture) is below the "
+                         "algorithmic bytes; hbm.dram_frac is the fraction of the measured copy peak the kernel really draws")
+    r.update({"workload": "ogbn-products look-alike: N=%d E=%d D=%d fp32" % (N, E, D), "edge_dim_per_s": E * D / (kernel_ms * 1e-3)})
+    return r
+
+
+def ref_gpu_epoch(args, gr, rp, ci, deg, pp, pn, device):
+    """The reference's OWN layer code (gnn_conv.py GCNConv, unchanged, from oracle/_ref/ref_py.zip) on the reference's OWN
+    kernels (GNNAdvisor_ref.so) in the epoch loop of GNNA_main.py:142-187, on the same graph and sizes as gcn_epoch_ms.
+    The group table is the exact one (the reference's own float32 build_part is corrupt beyond 2^24 edges)."""
+    import importlib.util
+    import tempfile
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    ref = build_ref.load_ref()
+    tmp = tempfile.mkdtemp(prefix="refpy_")
+    got = build_ref.unpack_py(tmp)
+    if ref is None or got is None:
+        return {"unavailable": "oracle/_ref artefacts not built"}
+    py_dir, _ = got
+    saved = {k: sys.modules.get(k) for k in ("GNNAdvisor", "param", "gnn_conv")}
+    sys.modules["GNNAdvisor"] = ref
+    sys.path.insert(0, py_dir)
+    try:
+        spec = importlib.util.spec_from_file_location("gnn_conv", os.path.join(py_dir, "gnn_conv.py"))
+        gc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(gc)
+    finally:
+        sys.path.remove(py_dir)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+    class Info:
+        pass
+    info = Info()
+    info.row_pointers, info.column_index, info.degrees, info.partPtr, info.part2Node = rp, ci, deg, pp, pn
+    info.partSize, info.dimWorker, info.warpPerBlock = args.part_size, args.dim_worker, args.warp_per_block
+    n = gr["num_nodes"]
+    x = torch.randn(n, gr["in_dim"], device=device)
+    y = torch.ones(n, dtype=torch.long, device=device)
+    c1, c2 = gc.GCNConv(gr["in_dim"], gr["hidden"]).to(device), gc.GCNConv(gr["hidden"], gr["classes"]).to(device)
+    opt = torch.optim.Adam(list(c1.parameters()) + list(c2.parameters()), lr=0.01)
+
+    def train():
+        opt.zero_grad()
+        h = F.relu(c1(x, info))
+        o = F.log_softmax(c2(h, info), dim=1)
+        F.nll_loss(o, y).backward()
+        opt.step()
+    k = 5
+    return {"ms": timed(train, k, 2) / k, "epochs_timed": k,
+            "what": "reference gnn_conv.GCNConv (unchanged) on the reference kernels recompiled for sm_100a, GCN %d-%d-%d, fwd+bwd+Adam"
+                    % (gr["in_dim"], gr["hidden"], gr["classes"])}
 
 
 def ref_gpu(args, X, rp, ci, deg, pp, pn, our_step, our_ms):

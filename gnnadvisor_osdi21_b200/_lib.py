@@ -77,8 +77,10 @@ SIGNATURES = {
     "gnna_halo_ack": (i32, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, i32, i32, ctypes.c_void_p]),
     "gnna_rabbit_reorder_host": (i32, [c_i32p, c_i32p, i64, i64, c_i32p]),
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
+    "gnna_probe_l2_read": (i32, [ctypes.c_void_p, i64, i32, i32, i32, ctypes.c_void_p, ctypes.c_void_p]),
     "gnna_launch_count": (i64, [i32]),
     "gnna_set_gcn_exact": (i32, [i32]),
+    "gnna_set_small_parts": (i64, [i64]),
     "gnna_set_staged": (i32, [i32]),
     "gnna_set_runs": (i32, [i32]),
     "gnna_query_runs": (i32, [i32, i32, i64, i64]),
@@ -118,6 +120,12 @@ def launch_count(reset=False):
 def set_gcn_exact(on):
     """True: per-edge rounding of the reference (bit-identical single-group rows); False: pre-scaled (default)."""
     return bool(load().gnna_set_gcn_exact(1 if on else 0))
+
+
+def set_small_parts(limit):
+    """Group tables of at most `limit` groups take the single-launch row-owned kernel (csrc/aggregate_small.cu); 0: never.
+    Returns the previous limit."""
+    return int(load().gnna_set_small_parts(int(limit)))
 
 
 def set_staged(on):

@@ -476,6 +476,19 @@ static bool staged_mode()
     return g_staged == 1;
 }
 
+// tables of at most this many groups take the single-launch path (GNNA_SMALL_PARTS; 0 switches it off).  16 K groups
+// of <= 32 neighbours are <= 0.5 M row reads: below that the general path's four stream operations cost more than its kernel.
+static long long g_small_parts = -1;
+static long long small_parts_limit()
+{
+    if (g_small_parts < 0) {
+        const char *e = getenv("GNNA_SMALL_PARTS");
+        g_small_parts = e ? atoll(e) : 16384;
+        if (g_small_parts < 0) g_small_parts = 0;
+    }
+    return g_small_parts;
+}
+
 int repack_rows(const float *X, float *Xs, const float *degrees, int64_t num_nodes, int dim, int ldx, cudaStream_t stream)
 {
     if (num_nodes == 0 || dim == 0) return GNNA_OK;
@@ -554,6 +567,14 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     GNNA_REQUIRE(ldx >= dim, "aggregate: ldx %d < dim %d", ldx, dim);
 
     GNNA_REQUIRE(num_parts == 0 || (row_ptr && col_idx && part_ptr && part2node), "aggregate: null index pointer");
+
+    // launch-bound graphs (Cora, citeseer): ONE kernel that owns rows, writes every row once -- no zero-fill, no
+    // pre-scale pass, no scratch (aggregate_small.cu)
+    if (elem_bytes == 4 && !accumulate && num_parts > 0 && num_parts <= small_parts_limit() && num_nodes <= 8 * small_parts_limit()) {
+        const int rc = aggregate_small(mode, (const float *)X, (float *)out, col_idx, degrees, eps, part_ptr, part2node,
+                                       (long long)num_nodes, (long long)num_parts, dim, ldx, gcn_exact_mode(), stream);
+        if (rc != GNNA_ERR_UNSUPPORTED) return rc;
+    }
 
     // fp32 pre-pass into stream-ordered scratch buffers when it pays:
     //   * default GCN rounding: pre-scale rows by degrees (no per-edge degree gather afterwards)
@@ -668,6 +689,13 @@ finish:
 }
 
 }  // namespace gnna
+
+extern "C" int64_t gnna_set_small_parts(int64_t limit)
+{
+    const long long prev = gnna::small_parts_limit();
+    gnna::g_small_parts = limit < 0 ? 0 : limit;
+    return prev;
+}
 
 extern "C" int gnna_set_staged(int on)
 {

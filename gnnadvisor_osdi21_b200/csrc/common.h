@@ -48,6 +48,11 @@ int aggregate_runs(int elem_bytes, const void *X, float *out, const int32_t *row
                    long long num_parts, int dim, int ldx, float scale, int flags, cudaStream_t stream);
 int runs_mode();
 
+// single-launch row-owned variant for launch-bound graphs (aggregate_small.cu); GNNA_ERR_UNSUPPORTED when the shape does not fit
+int aggregate_small(int mode, const float *X, float *out, const int32_t *col_idx, const float *degrees, float eps,
+                    const int32_t *part_ptr, const int32_t *part2node, long long num_nodes, long long num_parts, int dim, int ldx,
+                    bool exact_gcn, cudaStream_t stream);
+
 bool gcn_exact_mode();   // GNNA_GCN_EXACT / gnna_set_gcn_exact
 
 // Xs[i,:] = degrees[i] * X[i,:]  (X == Xs allowed)

@@ -48,6 +48,12 @@ static int get_handle(cublasHandle_t *h)
             return fail(GNNA_ERR_CUBLAS, "cublasCreate failed (%d)", (int)s);
         }
         cublasSetMathMode(g_handles[dev], CUBLAS_DEFAULT_MATH);    // plain fp32 SGEMM, TF32 stays off (as torch::mm)
+        // a workspace of our own: without one cuBLAS allocates stream-ordered memory behind the call, which a stream
+        // capture (main.py --cuda_graph, the multi-GPU step graphs) must not depend on
+        void *ws = nullptr;
+        const size_t ws_bytes = 32u << 20;
+        if (cudaMalloc(&ws, ws_bytes) == cudaSuccess) cublasSetWorkspace(g_handles[dev], ws, ws_bytes);
+        else (void)cudaGetLastError();
     }
     *h = g_handles[dev];
     return GNNA_OK;

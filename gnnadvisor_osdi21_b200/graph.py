@@ -100,6 +100,17 @@ def stream_pairs(num_nodes, start, count, kind="rmat", seed=20211, device="cpu",
     return src[keep], dst[keep]
 
 
+def stream_features(ids, dim, seed=20212):
+    """Feature rows of the given GLOBAL node ids: x[i, d] = a pure function of (seed, i, d), uniform in [-sqrt(3), sqrt(3))
+    (unit variance like dataset.py:129's randn) and exactly the same on every device, so a rank can produce the rows it
+    owns -- and a checker any row it likes -- without a feature file or an exchange.  Returns float32 [len(ids), dim]."""
+    ids = torch.as_tensor(ids).to(torch.int64).reshape(-1, 1)
+    cols = torch.arange(int(dim), dtype=torch.int64, device=ids.device).reshape(1, -1)
+    h = _mix64(_mix64(ids ^ _s64(int(seed) * _GOLD + 0x7654321)) + cols * _s64(_GOLD))
+    u = ((h >> 40) & 0xFFFFFF).to(torch.float32)                 # 24 bits: exact in float32
+    return (u * (2.0 ** -23) - 1.0) * 1.7320508
+
+
 def synth_graph(num_nodes, num_edges, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT, exact=True):
     """Symmetric graph with exactly 2*floor(num_edges/2) directed edges (when that many distinct
     pairs exist), no self loops, last node non-isolated.  Returns (row_ptr, col_idx)

@@ -286,12 +286,24 @@ typedef struct gnna_launch_info {
 GNNA_API int gnna_query_launch(int elem_bytes, int dim, int64_t num_parts, int dim_worker, int warp_per_block,
                       gnna_launch_info *info);
 
+/* Measurement infrastructure: read `bytes` of `buf` (a buffer that fits in L2) `passes` times with 128-bit loads that
+ * bypass L1 -- mode 0 a coalesced stream, mode 1 randomly ordered 256-byte rows (the D=64 fp32 gather's pattern).  Timed
+ * by the caller with CUDA events, it gives bench.py the L2 -> SM bandwidth of the box: the roof of the aggregation when
+ * the feature matrix is L2-resident.  `sink`: any 4 writable device bytes.  No reference counterpart.                */
+GNNA_API int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, int mode, int ctas_per_sm, void *sink, void *stream);
+
 /* GCN rounding: 0 (default) = out_i = n_i * sum_j (n_j * x_j): one pre-scale pass over the features,
  * then a weight-free gather (no per-edge degrees[nid] gather; each term within 2 roundings of the
  * reference's).  1 = the reference's per-edge fl(fl(n_i*n_j) * x_j) (kernel.cu:389,403), bit-identical
  * to it for every node whose neighbours fit one group.  Also settable with GNNA_GCN_EXACT=1 in the
  * environment.  Returns the previous setting.                                                  */
 GNNA_API int gnna_set_gcn_exact(int on);
+
+/* Group tables of at most `limit` groups (default 16384, GNNA_SMALL_PARTS in the environment; 0 = never) are aggregated by
+ * ONE kernel launch in which a sub-warp owns a destination row and writes it once -- no zero-fill, no pre-scale pass, no
+ * scratch allocation (csrc/aggregate_small.cu): the launch-latency-bound graphs (Cora, citeseer).  Same group-table
+ * semantics and rounding as the general path.  Returns the previous limit.                                    */
+GNNA_API int64_t gnna_set_small_parts(int64_t limit);
 
 /* 1 = use the persistent kernel that streams the group table and the column indices through TMA bulk copies
  * (cp.async.bulk) into a shared-memory ring (csrc/aggregate_staged.cu) where it applies (fp32, dim % 4 == 0,

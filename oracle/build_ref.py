@@ -60,6 +60,49 @@ def build(verbose=False):
     return SO
 
 
+REF_PY_DIR = "/root/reference/GNNAdvisor"
+PY_ZIP = os.path.join(OUT_DIR, "ref_py.zip")    # the reference's Python layer, byte for byte, as ONE git-ignored artefact
+REF_PY_FILES = ("gnn_conv.py", "param.py", "dataset.py", "GNNA_main.py", "unitest.py")
+_REFMOD = ('"""`import GNNAdvisor` -> the reference\'s own extension compiled for sm_100a (oracle/build_ref.py). CHECKER ONLY."""\n'
+           "import sys\n"
+           "sys.path.insert(0, %r)\n"
+           "import build_ref as _b\n"
+           "_m = _b.load_ref()\n"
+           "SAG, forward, backward, forward_gin, backward_gin, build_part = (\n"
+           "    _m.SAG, _m.forward, _m.backward, _m.forward_gin, _m.backward_gin, _m.build_part)\n")
+
+
+def stage_py():
+    """Pack the reference's own gnn_conv.py / param.py / dataset.py / GNNA_main.py / unitest.py UNCHANGED into
+    oracle/_ref/ref_py.zip -- a build artefact next to the compiled extension, git-ignored like it, never part of the
+    repository -- so that the GPU box, which has no /root/reference, can run the reference's scripts against this runtime
+    (tests/test_reference_gpu.py) and against the reference's own kernels (the R-GPU epoch baseline of bench.py)."""
+    import zipfile
+    if not os.path.isdir(REF_PY_DIR):
+        return os.path.exists(PY_ZIP)
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with zipfile.ZipFile(PY_ZIP, "w", zipfile.ZIP_DEFLATED) as z:
+        for f in REF_PY_FILES:
+            z.write(os.path.join(REF_PY_DIR, f), f)
+    return True
+
+
+def unpack_py(dest):
+    """Extract the staged reference scripts into `dest`/py (a scratch directory of the caller) and write `dest`/refmod/
+    GNNAdvisor.py, a loader that makes `import GNNAdvisor` resolve to GNNAdvisor_ref.so.  Returns (py_dir, refmod_dir) or None."""
+    import zipfile
+    if not os.path.exists(PY_ZIP):
+        return None
+    py_dir, refmod = os.path.join(dest, "py"), os.path.join(dest, "refmod")
+    os.makedirs(py_dir, exist_ok=True)
+    os.makedirs(refmod, exist_ok=True)
+    with zipfile.ZipFile(PY_ZIP) as z:
+        z.extractall(py_dir)
+    with open(os.path.join(refmod, "GNNAdvisor.py"), "w") as f:
+        f.write(_REFMOD % HERE)
+    return py_dir, refmod
+
+
 def load_ref():
     """Import the compiled reference as module `GNNAdvisor_ref` (or None if it is not built)."""
     if not os.path.exists(SO):
@@ -73,3 +116,4 @@ def load_ref():
 
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    print("reference python layer staged:", stage_py())

