@@ -79,17 +79,19 @@ def l2_peak_gbs(device=None):
     if device.index in _L2_PEAK:
         return _L2_PEAK[device.index]
     lib = _lib.load()
-    nbytes, passes = 32 << 20, 40
+    nbytes, passes = 40 << 20, 40
     with torch.cuda.device(device):
         buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
         sink = torch.zeros(1, dtype=torch.int32, device=device)
-        res = {"buffer_MB": nbytes >> 20, "passes": passes, "l2_size_MB": torch.cuda.get_device_properties(device).L2_cache_size / 2 ** 20}
+        res = {"buffer_MB_at_most": nbytes >> 20, "passes": passes, "l2_size_MB": torch.cuda.get_device_properties(device).L2_cache_size / 2 ** 20}
         for name, mode in (("seq", 0), ("rows256", 1)):
+            per_pass = ctypes.c_int64(0)
+
             def run():
                 _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), nbytes, passes, mode, 2, ctypes.c_void_p(sink.data_ptr()),
-                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2 probe")
+                                                  ctypes.byref(per_pass), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2 probe")
             best = min(timed(run, 1, 1) for _ in range(5))
-            res[name + "_GBs"] = nbytes * passes / (best * 1e-3) / 1e9
+            res[name + "_GBs"] = per_pass.value * passes / (best * 1e-3) / 1e9
     _L2_PEAK[device.index] = res
     return res
 
@@ -236,7 +238,7 @@ def config_of(args, N, E, P, world=1):
                   else "FIT in the 126 MB L2 (a launch-latency-bound configuration, not a bandwidth measurement)")}
     if world > 1:
         c["parallelism"] = ("1-D vertex-range shards x%d (cost-balanced: edges + %d per row), one halo exchange per aggregation"
-                            % (world, int(os.environ.get("GNNA_ROW_WEIGHT", default_row_weight(world)))))
+                            % (world, int(os.environ.get("GNNA_ROW_WEIGHT", default_row_weight(world, E / max(N, 1))))))
     return c
 
 

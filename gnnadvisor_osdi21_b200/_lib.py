@@ -72,12 +72,15 @@ SIGNATURES = {
     "gnna_halo_push_f32": (i32, [c_f32p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_void_p),
                                  ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
                                  i32, i32, i32, ctypes.c_void_p]),
+    "gnna_halo_push_ce": (i32, [c_f32p, i64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_void_p),
+                                ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
+                                i32, i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
     "gnna_halo_begin_step": (i32, [ctypes.c_void_p, ctypes.c_void_p]),
     "gnna_halo_wait": (i32, [ctypes.c_void_p, i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
     "gnna_halo_ack": (i32, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, i32, i32, ctypes.c_void_p]),
     "gnna_rabbit_reorder_host": (i32, [c_i32p, c_i32p, i64, i64, c_i32p]),
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
-    "gnna_probe_l2_read": (i32, [ctypes.c_void_p, i64, i32, i32, i32, ctypes.c_void_p, ctypes.c_void_p]),
+    "gnna_probe_l2_read": (i32, [ctypes.c_void_p, i64, i32, i32, i32, ctypes.c_void_p, ctypes.POINTER(i64), ctypes.c_void_p]),
     "gnna_launch_count": (i64, [i32]),
     "gnna_set_gcn_exact": (i32, [i32]),
     "gnna_set_small_parts": (i64, [i64]),

@@ -19,17 +19,24 @@ Layout (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU te
   * `degrees` of the halo nodes are fetched once at setup with the same exchange.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
 
 
-def default_row_weight(world):
-    """Cost of owning one row, in edge-equivalents, when cutting the vertex ranges.  A rank's step is
-    aggregation (proportional to its edges) plus halo traffic (every peer needs most of its rows on dense graphs:
-    proportional to rows * (world-1)).  Measured on 8xB200 (Reddit look-alike, D=64): 0.0154 ns per edge against
-    ~4 ns per row at 7 peers, i.e. ~40 edge-equivalents per row and peer."""
-    return 0 if world <= 1 else 40 * (world - 1)
+def default_row_weight(world, avg_degree=None):
+    """Cost of owning one row, in edge-equivalents, when cutting the vertex ranges.  A rank's step is aggregation
+    (proportional to its edges) plus halo traffic.  When the halo rows are gathered and pushed by a kernel (sparse halos)
+    every row a rank owns costs its SMs time once per peer that needs it -- measured on 8xB200 (D=64): 0.0154 ns per edge
+    against ~4 ns per row at 7 peers, i.e. ~40 edge-equivalents per row and peer.  On DENSE graphs (avg_degree / world >= 16:
+    every peer needs nearly every row, the blocks travel on the copy engines, csrc/halo.cu) rows cost the SMs nothing and
+    the cut balances edges alone."""
+    if world <= 1:
+        return 0
+    if avg_degree is not None and avg_degree / world >= 16:
+        return 0
+    return 40 * (world - 1)
 
 
 def partition_ranges(row_ptr, world, row_weight=0):
@@ -81,7 +88,7 @@ def _a2a(out, inp, out_splits, in_splits, group):
 class ShardedGraph:
     """This rank's shard of a graph every rank can see (replicated CSR in, sharded tables out)."""
 
-    def __init__(self, row_ptr, col_idx, part_size, device=None, group=None, ranges=None, row_weight=0):
+    def __init__(self, row_ptr, col_idx, part_size, device=None, group=None, ranges=None, row_weight=0, dense_halo=None):
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         device = torch.device(device) if device is not None else row_ptr.device
@@ -90,10 +97,10 @@ class ShardedGraph:
         e0, e1 = int(row_ptr[v0]), int(row_ptr[v1])
         rp_local = (row_ptr[v0:v1 + 1].to(torch.int64) - e0).to(device)
         self._setup(ranges, rp_local, col_idx[e0:e1].to(device), part_size, device, group,
-                    num_nodes_global=row_ptr.numel() - 1, num_edges_global=int(row_ptr[-1]))
+                    num_nodes_global=row_ptr.numel() - 1, num_edges_global=int(row_ptr[-1]), dense_halo=dense_halo)
 
     @classmethod
-    def from_rows(cls, ranges, row_ptr_local, cols_global, part_size, device=None, group=None):
+    def from_rows(cls, ranges, row_ptr_local, cols_global, part_size, device=None, group=None, dense_halo=None):
         """A shard built from the rank's OWN rows only (graph.synth_graph_shard, or a loader that reads a vertex range):
         row_ptr_local [n_local+1] offsets from 0, cols_global [E_local] GLOBAL neighbour ids.  No rank ever holds the
         whole graph; the global edge count is an all-reduce of the local ones (int64: it exceeds 2^31 for
@@ -104,10 +111,11 @@ class ShardedGraph:
         if dist.get_world_size(group) > 1:
             dist.all_reduce(e_local, group=group)
         self._setup(list(ranges), row_ptr_local.to(device), cols_global.to(device), part_size, device, group,
-                    num_nodes_global=int(ranges[-1]), num_edges_global=int(e_local.item()))
+                    num_nodes_global=int(ranges[-1]), num_edges_global=int(e_local.item()), dense_halo=dense_halo)
         return self
 
-    def _setup(self, ranges, rp_local, cols_global, part_size, device, group, num_nodes_global, num_edges_global):
+    def _setup(self, ranges, rp_local, cols_global, part_size, device, group, num_nodes_global, num_edges_global,
+               dense_halo=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -125,9 +133,23 @@ class ShardedGraph:
         bounds = torch.tensor(self.ranges, dtype=torch.int64, device=device)
         remote = (cols < v0) | (cols >= v1)
         halo = torch.unique(cols[remote])                                   # sorted => grouped by owner
+        owner = torch.searchsorted(bounds, halo, right=True) - 1
+        needed = [int(x) for x in torch.bincount(owner, minlength=self.world).cpu()]
+        # DENSE halos: when this rank needs at least `dense_halo` (default 0.75, GNNA_DENSE_HALO; 0 = never) of an owner's
+        # rows -- every pair does on a dense graph: 92 % on the Reddit look-alike at 8 GPUs -- it asks for the owner's WHOLE
+        # range.  The owner's block is then its local rows as they lie in memory and travels as one copy-engine memcpy
+        # over NVLink (csrc/halo.cu: gnna_halo_push_ce) instead of a gather kernel over an index list.
+        if dense_halo is None:
+            dense_halo = float(os.environ.get("GNNA_DENSE_HALO", "0.75"))
+        self.dense_from = [q != self.rank and dense_halo > 0 and self.ranges[q + 1] > self.ranges[q]
+                           and needed[q] >= dense_halo * (self.ranges[q + 1] - self.ranges[q]) for q in range(self.world)]
+        if any(self.dense_from):
+            halo = torch.unique(torch.cat([halo] + [torch.arange(self.ranges[q], self.ranges[q + 1], dtype=torch.int64, device=device)
+                                                    for q in range(self.world) if self.dense_from[q]]))
+            owner = torch.searchsorted(bounds, halo, right=True) - 1
+        self.halo_rows_needed = needed
         self.n_halo = int(halo.numel())
         self.halo_ids = halo
-        owner = torch.searchsorted(bounds, halo, right=True) - 1
         self.recv_counts = [int(x) for x in torch.bincount(owner, minlength=self.world).cpu()]
         local_cols = torch.where(remote, self.n_local + torch.searchsorted(halo, cols), cols - v0).to(torch.int32)
         del cols, remote
@@ -141,6 +163,8 @@ class ShardedGraph:
         self.send_counts = [int(x) for x in sc.cpu()]
         self.send_idx = torch.empty(sum(self.send_counts), dtype=torch.int64, device=device)
         _a2a(self.send_idx, want, self.send_counts, self.recv_counts, group)
+        # a peer that wants n_local distinct rows of mine wants all of them, in order: its block is my rows verbatim
+        self.dense_to = [p != self.rank and self.n_local > 0 and self.send_counts[p] == self.n_local for p in range(self.world)]
         self.n_ext = self.n_local + self.n_halo
         self._tables_built = False
         self.part_ptr = self.part2node = self.degrees_ext = None
@@ -371,6 +395,12 @@ class PeerHalo:
         self.c_dst_row0 = (ctypes.c_int64 * world)(*self.dst_row0)
         self.c_peer_ctrl = (ctypes.c_void_p * world)(*self.peer_ctrl)
         self.c_peer_buf = [(ctypes.c_void_p * world)(*self.peer_buf[b]) for b in range(2)]
+        # peers that asked for my whole range are served by the copy engines (GNNA_HALO_CE=0: always the push kernel)
+        self.dense_mask = 0
+        if os.environ.get("GNNA_HALO_CE", "1") == "1":
+            for p in range(world):
+                if sg.dense_to[p]:
+                    self.dense_mask |= 1 << p
         dist.barrier(group=group)
 
     def _view(self, parity, dim):
@@ -407,6 +437,15 @@ class PeerHalo:
         from . import _lib
         sg = self.sg
         b = self.step & 1
+        if self.dense_mask:
+            with torch.cuda.device(sg.device):
+                st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+                _lib.check(self.lib.gnna_halo_push_ce(ctypes.c_void_p(self.buf_ptr[b]), sg.n_local,
+                                                      ctypes.c_void_p(sg.send_idx.data_ptr() if sg.send_idx.numel() else 0),
+                                                      self.send_begin, self.c_peer_buf[b], self.c_peer_ctrl, self.c_dst_row0,
+                                                      ctypes.c_void_p(self.ctrl_ptr), sg.world, sg.rank, self.cur_dim,
+                                                      self.dense_mask, st), "halo_push_ce")
+            return self._view(b, self.cur_dim)
         with torch.cuda.device(sg.device):
             st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
             _lib.check(self.lib.gnna_halo_push_f32(ctypes.c_void_p(self.buf_ptr[b]),

@@ -30,10 +30,11 @@ def run(args, bench):
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
 
-    row_weight = int(os.environ.get("GNNA_ROW_WEIGHT", gdist.default_row_weight(world)))
     D = args.dim
     n_all, e_all, in_dim, hidden, classes, kind = graph.LOOKALIKES[args.workload]
     n_all, e_all = max(2, int(n_all * args.scale)), max(2, int(e_all * args.scale))
+    # the config line (and the reference arm's) computes the same weight from the same two numbers
+    row_weight = int(os.environ.get("GNNA_ROW_WEIGHT", gdist.default_row_weight(world, e_all / n_all)))
     # graphs that do not fit one GPU are generated SHARD BY SHARD: every rank walks the same counter-based pair stream and
     # keeps the rows it owns (graph.synth_graph_shard); nobody ever holds the whole graph.  Smaller ones (Reddit) keep the
     # exact edge count of the dataset, which needs a global duplicate count: built whole on every GPU, then cut.
@@ -78,7 +79,9 @@ def run(args, bench):
     if want_peer:
         try:
             peer = gdist.PeerHalo(sg, D)
-            halo_mode = "NVLink push kernel over CUDA IPC (gnna_halo_push_f32)"
+            n_dense = bin(peer.dense_mask).count("1")
+            halo_mode = ("CUDA-IPC mapped peer buffers over NVLink: copy-engine memcpy of the whole range to %d dense peer(s) "
+                         "(gnna_halo_push_ce), push kernel for %d sparse one(s) (gnna_halo_push_f32)" % (n_dense, world - 1 - n_dense))
         except Exception as e:   # noqa: BLE001
             peer, halo_mode = None, "nccl all_to_all_single (peer mapping failed: %s)" % str(e)[:80]
     ok = torch.tensor([1 if peer is not None else 0], device=device)
@@ -284,7 +287,7 @@ def run(args, bench):
             epoch = {"error": str(e)[:200]}
 
     halo = sg.halo_bytes(D)
-    stats = torch.tensor([sg.num_edges_local, sg.n_local, sg.n_halo, P_local, halo["recv"], halo["send"]],
+    stats = torch.tensor([sg.num_edges_local, sg.n_local, sg.n_halo, P_local, halo["recv"], halo["send"], sum(sg.halo_rows_needed)],
                          device=device, dtype=torch.float64)
     allstats = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(allstats, stats)
@@ -320,7 +323,7 @@ def run(args, bench):
                            "oracle_check": "up to 2048 rows per rank, chosen at random, recomputed by the CPU oracle from features "
                                            "regenerated from their GLOBAL ids (max over ranks, tolerance 1e-4)",
                            "gcn_epoch_ms": epoch,
-                           "shards": [{"edges": int(s[0]), "rows": int(s[1]), "halo_rows": int(s[2]),
+                           "shards": [{"edges": int(s[0]), "rows": int(s[1]), "halo_rows": int(s[2]), "halo_rows_needed": int(s[6]),
                                        "halo_recv_bytes": int(s[4]), "halo_send_bytes": int(s[5])} for s in per_rank]}}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -241,6 +241,15 @@ GNNA_API int gnna_ipc_open(const unsigned char *handle64, void **ptr);
 GNNA_API int gnna_ipc_close(void *ptr);
 GNNA_API int gnna_ipc_free(void *ptr);
 
+/* gnna_halo_push_f32 for DENSE halos: a peer whose bit (by rank) is set in dense_mask asked for ALL n_local rows of this
+ * rank (its block for this rank is the rank's local rows as they lie in memory) and gets them as ONE device-to-device
+ * cudaMemcpyAsync over NVLink on the copy engines -- no SM, no index list; peers not in the mask are served by the push
+ * kernel from their send lists.  Same flags / acknowledgements / step counter as gnna_halo_push_f32.          */
+GNNA_API int gnna_halo_push_ce(const float *x_local, int64_t n_local, const int64_t *send_idx, const int32_t *send_begin_host,
+                               void *const *peer_feature_base_host, void *const *peer_ctrl_host,
+                               const int64_t *peer_dst_row0_host, void *my_ctrl,
+                               int world, int my_rank, int dim, uint32_t dense_mask, void *stream);
+
 /* One exchange step = begin_step, push, wait, (aggregate), ack.  The step number (1, 2, 3, ...) lives in the
  * control block and is read on the device, so a step captured in a CUDA graph can be replayed.
  * begin_step: first thing on the compute stream: step += 1.
@@ -289,8 +298,10 @@ GNNA_API int gnna_query_launch(int elem_bytes, int dim, int64_t num_parts, int d
 /* Measurement infrastructure: read `bytes` of `buf` (a buffer that fits in L2) `passes` times with 128-bit loads that
  * bypass L1 -- mode 0 a coalesced stream, mode 1 randomly ordered 256-byte rows (the D=64 fp32 gather's pattern).  Timed
  * by the caller with CUDA events, it gives bench.py the L2 -> SM bandwidth of the box: the roof of the aggregation when
- * the feature matrix is L2-resident.  `sink`: any 4 writable device bytes.  No reference counterpart.                */
-GNNA_API int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, int mode, int ctas_per_sm, void *sink, void *stream);
+ * the feature matrix is L2-resident.  `bytes` is rounded down to whole batches of the grid; *bytes_per_pass = what one pass
+ * reads.  `sink`: any 4 writable device bytes.  No reference counterpart.                                       */
+GNNA_API int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, int mode, int ctas_per_sm, void *sink,
+                                int64_t *bytes_per_pass, void *stream);
 
 /* GCN rounding: 0 (default) = out_i = n_i * sum_j (n_j * x_j): one pre-scale pass over the features,
  * then a weight-free gather (no per-edge degrees[nid] gather; each term within 2 roundings of the

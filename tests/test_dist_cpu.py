@@ -29,7 +29,7 @@ def _worker(rank, world, port, ret):
         rp, ci = make_graph("rmat", n, 30000, 61)
         X = rand_features(n, dim, 62)
         deg = oracle.degrees(rp)
-        sg = gdist.ShardedGraph(torch.from_numpy(rp), torch.from_numpy(ci), ps, device="cpu").build_tables()
+        sg = gdist.ShardedGraph(torch.from_numpy(rp), torch.from_numpy(ci), ps, device="cpu", dense_halo=0).build_tables()
         v = sg.ranges
         assert v[0] == 0 and v[-1] == n and all(a <= b for a, b in zip(v, v[1:]))
         assert sg.n_local == v[rank + 1] - v[rank]
@@ -56,6 +56,32 @@ def _worker(rank, world, port, ret):
             loc = oracle.aggregate(mode, x_ext.numpy(), sg.col_idx.numpy(), sg.degrees_ext.numpy(), 0.5,
                                    sg.part_ptr.numpy(), sg.part2node.numpy())[:sg.n_local]
             assert np.array_equal(loc, full[v[rank]:v[rank + 1]]), "mode %d" % mode
+        # dense halos: an owner most of whose rows are needed is asked for its whole range (one contiguous block);
+        # the aggregation is unchanged, the owner sees "this peer wants all my rows, in order"
+        sd = gdist.ShardedGraph(torch.from_numpy(rp), torch.from_numpy(ci), ps, device="cpu", dense_halo=0.05).build_tables()
+        assert any(sd.dense_from) and not sd.dense_from[rank]
+        hd = sd.halo_ids.numpy()
+        assert set(remote).issubset(set(hd)) and np.array_equal(hd, np.unique(hd))
+        for q in range(world):
+            if sd.dense_from[q]:
+                assert sd.recv_counts[q] == v[q + 1] - v[q] and sd.halo_rows_needed[q] <= sd.recv_counts[q]
+        flags = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(flags, torch.tensor([int(f) for f in sd.dense_from]))
+        for p in range(world):                                   # what I see as a sender == what the receivers decided
+            assert bool(flags[p][rank]) == (sd.dense_to[p] and p != rank)
+            if sd.dense_to[p]:
+                lo = sum(sd.send_counts[:p])
+                assert torch.equal(sd.send_idx[lo:lo + sd.n_local], torch.arange(sd.n_local))
+        xd = sd.new_features(dim)
+        sd.local(xd).copy_(torch.from_numpy(X[v[rank]:v[rank + 1]]))
+        sd.exchange(xd)
+        l2g_d = np.concatenate([np.arange(v[rank], v[rank + 1]), hd])
+        assert np.array_equal(xd.numpy(), X[l2g_d])
+        for mode in (0, 1, 2):
+            full = oracle.aggregate(mode, X, ci, deg, 0.5, pp, pn)
+            loc = oracle.aggregate(mode, xd.numpy(), sd.col_idx.numpy(), sd.degrees_ext.numpy(), 0.5,
+                                   sd.part_ptr.numpy(), sd.part2node.numpy())[:sd.n_local]
+            assert np.array_equal(loc, full[v[rank]:v[rank + 1]]), "dense halo, mode %d" % mode
         # dW reduction helper
         w = torch.full((3, 2), float(rank + 1))
         gdist.allreduce_weight_grad(w)
@@ -92,3 +118,4 @@ def test_partition_ranges_balance_edges_not_nodes():
     rows_e = [v[i + 1] - v[i] for i in range(4)]
     rows_w = [w[i + 1] - w[i] for i in range(4)]
     assert max(rows_w) < max(rows_e) and gdist.default_row_weight(1) == 0 and gdist.default_row_weight(8) == 280
+    assert gdist.default_row_weight(8, avg_degree=492) == 0 and gdist.default_row_weight(8, avg_degree=14.5) == 280

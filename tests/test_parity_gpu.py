@@ -774,6 +774,8 @@ def test_small_path_all_modes_bit_identical_to_the_oracle(gname, dim):
 def test_small_path_every_row_is_written_once(ps):
     """No zero-fill launch: rows without neighbours at the head, in the middle and at the tail must come out zero even
     when the output buffer held garbage; F6 tables (terminal 0) drop the last group as the reference does."""
+    from gnnadvisor_osdi21_b200 import _lib as _l
+    _l.set_small_parts(1 << 20)                         # partSize 1 makes a 17 K-group table: keep it on the single-launch path
     rng = np.random.default_rng(31)
     deg = rng.integers(0, 70, 500)
     deg[:7] = 0; deg[100:160] = 0; deg[-9:] = 0; deg[-10] = 45; deg[250] = 1900          # a hub of many groups too
