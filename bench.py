@@ -480,6 +480,15 @@ def run_single(args):
             extras["gcn_epoch_ms_bf16_gather"] = gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, gather_dtype="bf16")
         except Exception as e:   # noqa: BLE001
             extras["gcn_epoch_ms_bf16_gather"] = {"error": str(e)}
+        # GIN-5 on the same graph: the model whose forward is aggregate -> product, i.e. where the fused
+        # tcgen05 tile of BASELINE.json's config #3 applies (for the 2-layer GCN the only aggregate -> product with a
+        # gradient is layer 2's backward, whose aggregated width is the 41 classes: no tile of that width)
+        for key, kw in (("gin_epoch_ms", {}), ("gin_epoch_ms_bf16_gather", {"gather_dtype": "bf16"}),
+                        ("gin_epoch_ms_bf16_gather_fused", {"gather_dtype": "bf16", "fused": True})):
+            try:
+                extras[key] = gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, model="gin", **kw)
+            except Exception as e:   # noqa: BLE001
+                extras[key] = {"error": str(e)[:200]}
         # the reference's own CUDA kernels, recompiled for sm_100a, on the same tensors
         try:
             extras["ref_gpu"] = ref_gpu(args, X, rp, ci, deg, pp, pn, step, ms)
@@ -505,7 +514,7 @@ def run_single(args):
     print(json.dumps(line))
 
 
-def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, gather_dtype="fp32"):
+def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, gather_dtype="fp32", model="gcn", fused=False):
     import torch.nn.functional as F
     from gnnadvisor_osdi21_b200 import layers
 
@@ -517,20 +526,33 @@ def gcn_epoch_ms(args, gr, rp, ci, deg, pp, pn, device, gather_dtype="fp32"):
     n = gr["num_nodes"]
     x = torch.randn(n, gr["in_dim"], device=device)
     y = torch.ones(n, dtype=torch.long, device=device)
-    c1 = layers.GCNConv(gr["in_dim"], gr["hidden"], gather_dtype=gather_dtype).to(device)
-    c2 = layers.GCNConv(gr["hidden"], gr["classes"], gather_dtype=gather_dtype).to(device)
-    opt = torch.optim.Adam(list(c1.parameters()) + list(c2.parameters()), lr=0.01)
+    # GNNA_main.py:142-171: GCN = 2 convs, GIN = 5 convs (in-hid, hid-hid x3, hid-classes)
+    dims = [gr["in_dim"], gr["hidden"], gr["classes"]] if model == "gcn" else [gr["in_dim"]] + [gr["hidden"]] * 4 + [gr["classes"]]
+    conv = layers.GCNConv if model == "gcn" else layers.GINConv
+    convs = torch.nn.ModuleList([conv(a, b, gather_dtype=gather_dtype, fused=fused) for a, b in zip(dims[:-1], dims[1:])]).to(device)
+    opt = torch.optim.Adam(convs.parameters(), lr=0.01)
+    if model == "gin":
+        x = x * 1e-3        # five un-normalised sums over ~500 neighbours each: keep the activations finite
 
     def train():
         opt.zero_grad()
-        h = F.relu(c1(x, info))
-        o = F.log_softmax(c2(h, info), dim=1)
-        F.nll_loss(o, y).backward()
+        h = x
+        for i, c in enumerate(convs):
+            h = c(h, info)
+            if i < len(convs) - 1:
+                h = F.relu(h)
+        F.nll_loss(F.log_softmax(h, dim=1), y).backward()
         opt.step()
     k = max(3, min(args.steps // 5, 20))
+    fused_layers = 0
+    if fused:
+        for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+            width = a if model == "gin" else b
+            fused_layers += int(layers.fused_tile_supported(width, gather_dtype) and (model == "gin" or i > 0))
     return {"ms": timed(train, k, 3) / k, "epochs_timed": k,
-            "model": "GCN %d-%d-%d, fwd+bwd+Adam (GNNA_main.py:142-202), gathered rows %s"
-                     % (gr["in_dim"], gr["hidden"], gr["classes"], gather_dtype)}
+            "model": "%s %s, fwd+bwd+Adam (GNNA_main.py:142-202), gathered rows %s%s"
+                     % (model.upper(), "-".join(str(d) for d in dims), gather_dtype,
+                        ", aggregate->product fused on the tensor cores in %d of %d layers" % (fused_layers, len(dims) - 1) if fused else "")}
 
 
 def hbm_bound_leg(args, device):

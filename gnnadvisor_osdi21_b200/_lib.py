@@ -42,6 +42,8 @@ SIGNATURES = {
                               + [i32, i64] + _TUNE),
     "gnna_aggregate_part_f32_ex": (i32, [i32, i32, c_f32p, i64, c_f32p, i64] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
                                    + [i32, i64] + _TUNE),
+    "gnna_aggregate_gated_f32": (i32, [i32, c_f32p, i64, c_f32p, i64] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS
+                                 + [i32, i64, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), i32, ctypes.c_void_p] + _TUNE),
     "gnna_prescale_rows_f32": (i32, [c_f32p, c_f32p, c_f32p, i64, i32, ctypes.c_void_p]),
     "gnna_sgemm_f32": (i32, [i32, i32, i64, i64, i64, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
     "gnna_aggregate_bf16": (i32, [i32, ctypes.c_void_p, c_f32p] + _GRAPH + [c_f32p, ctypes.c_float] + _PARTS

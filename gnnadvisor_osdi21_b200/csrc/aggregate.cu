@@ -120,10 +120,34 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
                  const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                  const float *__restrict__ degrees,
                  const int32_t *__restrict__ part_ptr, const int32_t *__restrict__ part2node,
-                 long long num_parts, int dim, int ldx, float scale, int flags)
+                 long long num_parts, int dim, int ldx, float scale, int flags, const GateParams gate)
 {
     // dim = row stride of `out` (% VEC == 0, 16-byte aligned rows); ldx = row stride of X in elements (>= dim)
     constexpr int S = 32 / LPR;                      // neighbour-groups per warp
+    // Sharded path, exchange fused into the aggregation (common.h: GateParams): the rows of a peer are still crossing
+    // NVLink when this kernel starts.  A CTA whose groups gather a peer's rows waits for that peer's flag -- set by the
+    // peer's push after its last remote store (release, system scope) -- before it touches them; CTAs are dispatched in
+    // group order and the segments are ordered by arrival, so the SMs aggregate what is there while the rest lands.
+    if (gate.nseg > 0) {
+        if (threadIdx.x == 0) {
+            const long long per_cta = (long long)(blockDim.x >> 5) * S;
+            const long long g0 = (long long)blockIdx.x * per_cta;
+            const long long g1 = g0 + per_cta < num_parts ? g0 + per_cta : num_parts;
+            const unsigned step = *reinterpret_cast<const volatile unsigned *>(gate.step_ptr);
+            for (int sgm = 0; sgm < gate.nseg; sgm++) {
+                if (gate.peer[sgm] < 0 || g0 >= gate.bounds[sgm + 1] || g1 <= gate.bounds[sgm]) continue;
+                const unsigned *f = gate.flags + gate.peer[sgm];
+                unsigned v;
+                const long long t0 = clock64();
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    if (v >= step) break;
+                    if (clock64() - t0 > 8000000000LL) { atomicExch(gate.error_word, 2u); break; }
+                } while (true);
+            }
+        }
+        __syncthreads();
+    }
     // neighbour ids fetched per lane per batch: 32 neighbours per batch (8 at most per lane); the exact-GCN
     // variant also carries a weight per id and keeps the short batch (it is about rounding, not speed)
     constexpr int IPL_SHORT = (LPR >= 8) ? 1 : 8 / LPR;
@@ -403,11 +427,14 @@ static Geometry choose_geometry(int elem_bytes, int dim, long long num_parts, in
 template <typename T, int VEC, int LPR, int KCH, bool W>
 static cudaError_t launch(const Geometry &g, cudaStream_t st, const void *X, float *out, const int32_t *row_ptr,
                           const int32_t *col_idx, const float *deg, const int32_t *pp, const int32_t *pn,
-                          long long P, int dim, int ldx, float scale, int flags)
+                          long long P, int dim, int ldx, float scale, int flags, const GateParams *gate)
 {
     dim3 grid((unsigned)g.gx, (unsigned)g.gy, 1), block(g.wpb * 32, 1, 1);
+    GateParams gp;
+    if (gate) gp = *gate;
+    else gp.nseg = 0;
     aggregate_kernel<T, VEC, LPR, KCH, W><<<grid, block, 0, st>>>(reinterpret_cast<const T *>(X), out, row_ptr, col_idx,
-                                                                  deg, pp, pn, P, dim, ldx, scale, flags);
+                                                                  deg, pp, pn, P, dim, ldx, scale, flags, gp);
     return cudaGetLastError();
 }
 
@@ -552,7 +579,7 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
               const int32_t *part_ptr, const int32_t *part2node,
               int64_t num_nodes, int dim, int64_t num_parts,
               int part_size, int dim_worker, int warp_per_block, cudaStream_t stream, int ldx, int64_t num_rows_x,
-              bool accumulate)
+              bool accumulate, const GateParams *gate)
 {
     (void)part_size;  // group length is read from part_ptr; any table with sorted groups works
     GNNA_REQUIRE(mode >= MODE_SAG && mode <= MODE_GCN_PRESCALED, "aggregate: bad mode %d", mode);
@@ -570,7 +597,7 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
 
     // launch-bound graphs (Cora, citeseer): ONE kernel that owns rows, writes every row once -- no zero-fill, no
     // pre-scale pass, no scratch (aggregate_small.cu)
-    if (elem_bytes == 4 && !accumulate && num_parts > 0 && num_parts <= small_parts_limit() && num_nodes <= 8 * small_parts_limit()) {
+    if (elem_bytes == 4 && !accumulate && !gate && num_parts > 0 && num_parts <= small_parts_limit() && num_nodes <= 8 * small_parts_limit()) {
         const int rc = aggregate_small(mode, (const float *)X, (float *)out, col_idx, degrees, eps, part_ptr, part2node,
                                        (long long)num_nodes, (long long)num_parts, dim, ldx, gcn_exact_mode(), stream);
         if (rc != GNNA_ERR_UNSUPPORTED) return rc;
@@ -639,7 +666,7 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     float *o = reinterpret_cast<float *>(out);
     cudaError_t e;
     // opt-in: persistent kernel with the integer streams staged through TMA bulk copies (aggregate_staged.cu)
-    if (staged_mode() && elem_bytes == 4 && !weighted && ldx == dim && g.gy == 1) {
+    if (staged_mode() && !gate && elem_bytes == 4 && !weighted && ldx == dim && g.gy == 1) {
         const int rc = aggregate_staged((const float *)X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
                                         (long long)num_parts, 0x7fffffffffffffffLL, dim, part_size, scale, flags, stream);
         if (rc != GNNA_ERR_UNSUPPORTED) {
@@ -649,7 +676,7 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
         }
     }
     // run-based software-pipelined kernel (aggregate_runs.cu) where the library's rule or the caller selects it
-    if (runs_mode() != 0 && !weighted) {
+    if (runs_mode() != 0 && !weighted && !gate) {
         const int rc = aggregate_runs(elem_bytes, X, o, row_ptr, col_idx, degrees, part_ptr, part2node, (long long)num_nodes,
                                       (long long)num_parts, dim, ldx, scale, flags & (F_SCALE | F_ROWSCALE), stream);
         if (rc != GNNA_ERR_UNSUPPORTED) {
@@ -661,17 +688,17 @@ int aggregate(int mode, int elem_bytes, const void *X, void *out,
     if (elem_bytes == 4) {
         if (weighted)
             e = dispatch_lpr<float, 4, true>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                             (long long)num_parts, dim, ldx, scale, flags);
+                                             (long long)num_parts, dim, ldx, scale, flags, gate);
         else
             e = dispatch_lpr<float, 4, false>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                              (long long)num_parts, dim, ldx, scale, flags);
+                                             (long long)num_parts, dim, ldx, scale, flags, gate);
     } else {
         if (weighted)
             e = dispatch_vec<__nv_bfloat16, true>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                                  (long long)num_parts, dim, ldx, scale, flags);
+                                                  (long long)num_parts, dim, ldx, scale, flags, gate);
         else
             e = dispatch_vec<__nv_bfloat16, false>(g, stream, X, o, row_ptr, col_idx, degrees, part_ptr, part2node,
-                                                   (long long)num_parts, dim, ldx, scale, flags);
+                                                  (long long)num_parts, dim, ldx, scale, flags, gate);
     }
     count_launch(1);
 finish:

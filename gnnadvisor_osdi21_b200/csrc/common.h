@@ -28,13 +28,27 @@ void count_launch(int n = 1);               // thread-local launch counter
 
 enum Mode { MODE_SAG = 0, MODE_GCN = 1, MODE_GIN = 2, MODE_GCN_PRESCALED = 3 };
 
+// Gate of the fused exchange+aggregation kernel of the sharded path (aggregate.cu: aggregate_kernel, halo.cu): the group
+// table is the concatenation of one segment per OWNER of the neighbours; a CTA whose groups lie in a peer's segment waits
+// (acquire, system scope, bounded) until that peer's rows of the current step have landed in this rank's buffer.
+// nseg == 0: no gate (every single-GPU launch).
+constexpr int GATE_MAX_SEGS = 16;
+struct GateParams {
+    long long bounds[GATE_MAX_SEGS + 1];   // segment s = groups [bounds[s], bounds[s+1])
+    int peer[GATE_MAX_SEGS];               // rank whose flag gates segment s; -1: this rank's own rows, no wait
+    int nseg;
+    const unsigned *flags;                 // flags[q] >= step  <=>  rank q's rows of this step have arrived
+    const unsigned *step_ptr;
+    unsigned *error_word;
+};
+
 // One aggregation launch (aggregate.cu).  elem: 4 = fp32, 2 = bf16.
 int aggregate(int mode, int elem_bytes, const void *X, void *out,
               const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
               const int32_t *part_ptr, const int32_t *part2node,
               int64_t num_nodes, int dim, int64_t num_parts,
               int part_size, int dim_worker, int warp_per_block, cudaStream_t stream,
-              int ldx = 0, int64_t num_rows_x = 0, bool accumulate = false);
+              int ldx = 0, int64_t num_rows_x = 0, bool accumulate = false, const GateParams *gate = nullptr);
 
 // persistent TMA-staged variant (aggregate_staged.cu); GNNA_ERR_UNSUPPORTED when the shape has no such variant
 int aggregate_staged(const float *X, float *out, const int32_t *row_ptr, const int32_t *col_idx, const float *degrees,

@@ -10,6 +10,7 @@
 #include <cublas_v2.h>
 
 #include <mutex>
+#include <string.h>
 
 #include "common.h"
 
@@ -154,6 +155,42 @@ extern "C" int gnna_aggregate_part_f32_ex(int mode, int accumulate, const float 
     return aggregate(mode, 4, X, out, row_ptr, col_idx, degrees, eps, part_ptr, part2node, num_dst_rows, dim,
                      num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream, dim, num_src_rows,
                      accumulate != 0);
+}
+
+// The sharded step with the halo exchange FUSED into the aggregation (dist.ShardedGraph.aggregate_overlapped): ONE launch
+// over the concatenation of the per-owner sub-CSRs of a rank; the CTAs of a peer's segment wait inside the kernel for that
+// peer's flag in the halo control block (csrc/halo.cu) while the CTAs ahead of them aggregate what has already landed.
+// out is zero-filled, every group is merged with reductions.  mode 0 SAG, 2 GIN, 3 GCN on pre-scaled rows; dim % 4 == 0.
+extern "C" int gnna_aggregate_gated_f32(int mode, const float *X, int64_t num_src_rows, float *out, int64_t num_dst_rows,
+                                        const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
+                                        const int32_t *part_ptr, const int32_t *part2node, int dim, int64_t num_parts,
+                                        const int64_t *seg_bounds_host, const int32_t *seg_peer_host, int num_segs,
+                                        void *my_ctrl, int part_size, int dim_worker, int warp_per_block, void *stream)
+{
+    GNNA_REQUIRE(mode == MODE_SAG || mode == MODE_GIN || mode == MODE_GCN_PRESCALED,
+                 "gnna_aggregate_gated_f32: mode %d not supported (0, 2, 3)", mode);
+    GNNA_REQUIRE(dim % 4 == 0 && (((uintptr_t)X | (uintptr_t)out) & 15) == 0, "gnna_aggregate_gated_f32: dim %% 4 != 0 or unaligned");
+    GNNA_REQUIRE(num_segs >= 1 && num_segs <= GATE_MAX_SEGS && seg_bounds_host && seg_peer_host && my_ctrl,
+                 "gnna_aggregate_gated_f32: bad segment description");
+    GNNA_REQUIRE(seg_bounds_host[0] == 0 && seg_bounds_host[num_segs] == num_parts, "gnna_aggregate_gated_f32: segments do not cover the table");
+    GateParams gp;
+    memset(&gp, 0, sizeof(gp));
+    for (int s = 0; s < num_segs; s++) {
+        GNNA_REQUIRE(seg_bounds_host[s] <= seg_bounds_host[s + 1], "gnna_aggregate_gated_f32: segment bounds not ascending");
+        gp.bounds[s] = seg_bounds_host[s];
+        gp.peer[s] = seg_peer_host[s];
+    }
+    gp.bounds[num_segs] = seg_bounds_host[num_segs];
+    gp.nseg = num_segs;
+    unsigned *ctrl = (unsigned *)my_ctrl;          // layout: halo.cu (flags [0..15], error word [48], step [49])
+    gp.flags = ctrl;
+    gp.error_word = ctrl + 48;
+    gp.step_ptr = ctrl + 49;
+    GNNA_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)num_dst_rows * (size_t)dim, (cudaStream_t)stream));
+    if (num_parts == 0) return GNNA_OK;
+    return aggregate(mode, 4, X, out, row_ptr, col_idx, degrees, eps, part_ptr, part2node, num_dst_rows, dim,
+                     num_parts, part_size, dim_worker, warp_per_block, (cudaStream_t)stream, dim, num_src_rows,
+                     true, &gp);
 }
 
 extern "C" int gnna_prescale_rows_f32(const float *X, float *Xs, const float *degrees, int64_t num_rows, int dim, void *stream)

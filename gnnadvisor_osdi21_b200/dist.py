@@ -139,8 +139,11 @@ class ShardedGraph:
         # rows -- every pair does on a dense graph: 92 % on the Reddit look-alike at 8 GPUs -- it asks for the owner's WHOLE
         # range.  The owner's block is then its local rows as they lie in memory and travels as one copy-engine memcpy
         # over NVLink (csrc/halo.cu: gnna_halo_push_ce) instead of a gather kernel over an index list.
+        # Measured on 4xB200 (profiles/r02_v2_sweep_4gpu.txt): the copy-engine exchange frees the SMs (step 0.439 vs 0.448 ms)
+        # but competes with the H2D/D2H copies of an end-to-end step (e2e 0.89 vs 0.69 ms), so it is opt-in:
+        # GNNA_HALO_CE=1 (and then GNNA_DENSE_HALO, default 0.75, is the density from which a whole range is requested).
         if dense_halo is None:
-            dense_halo = float(os.environ.get("GNNA_DENSE_HALO", "0.75"))
+            dense_halo = float(os.environ.get("GNNA_DENSE_HALO", "0.75")) if os.environ.get("GNNA_HALO_CE", "0") == "1" else 0.0
         self.dense_from = [q != self.rank and dense_halo > 0 and self.ranges[q + 1] > self.ranges[q]
                            and needed[q] >= dense_halo * (self.ranges[q + 1] - self.ranges[q]) for q in range(self.world)]
         if any(self.dense_from):
@@ -230,8 +233,23 @@ class ShardedGraph:
             rp[1:] = torch.cumsum(torch.bincount(rows[m], minlength=n_local), 0)
             rp = rp.to(torch.int32).contiguous()
             ci = cols[m].to(torch.int32).contiguous()
-            pp, pn = ops.build_part_exact(self.part_size, rp)
+            # a row's neighbours are split over `world` sub-CSRs, so its groups are shorter than in the whole CSR; a larger
+            # group size for the sub-shards (GNNA_OWNER_PS) trades that fragmentation against balance
+            pp, pn = ops.build_part_exact(int(os.environ.get("GNNA_OWNER_PS", self.part_size)), rp)
             self.owner_shards.append((rp, ci, pp, pn))
+        # the same sub-shards as ONE group table, segment after segment in arrival order: what the fused
+        # exchange+aggregation kernel walks (gnna_aggregate_gated_f32)
+        e_off, g_off, pps, bounds = 0, 0, [], [0]
+        for rp, ci, pp, pn in self.owner_shards:
+            pps.append(pp[:-1].to(torch.int64) + e_off)
+            e_off += int(ci.numel())
+            g_off += int(pn.numel())
+            bounds.append(g_off)
+        self.gated_col = torch.cat([sh[1] for sh in self.owner_shards]).contiguous()
+        self.gated_pp = torch.cat(pps + [torch.tensor([e_off], dtype=torch.int64, device=dev)]).to(torch.int32).contiguous()
+        self.gated_pn = torch.cat([sh[3] for sh in self.owner_shards]).contiguous()
+        self.gated_bounds = (ctypes.c_int64 * (world + 1))(*bounds)
+        self.gated_peer = (ctypes.c_int32 * world)(*[-1 if q == rank else q for q in self.owner_order])
         return self
 
     def write_local(self, peer, x_local, prescale):
@@ -269,6 +287,16 @@ class ShardedGraph:
         kmode = 3 if mode == 1 else mode
         p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
         st = ctypes.c_void_p(cur.cuda_stream)
+        if os.environ.get("GNNA_GATED", "1") == "1":
+            # ONE kernel: the CTAs of a peer's segment wait for that peer's flag inside the kernel (csrc/aggregate.cu)
+            _lib.check(lib.gnna_aggregate_gated_f32(kmode, p(x_ext), self.n_ext, p(out), self.n_local, p(self.row_ptr),
+                                                    p(self.gated_col), p(self.degrees_ext) if kmode == 3 else ctypes.c_void_p(0),
+                                                    float(eps), p(self.gated_pp), p(self.gated_pn), d, self.gated_pn.numel(),
+                                                    self.gated_bounds, self.gated_peer, self.world, ctypes.c_void_p(peer.ctrl_ptr),
+                                                    self.part_size, int(dim_worker), int(warp_per_block), st), "gated aggregate")
+            peer.ack()
+            cur.wait_event(self._ev_pushed)
+            return out
         for k, (q, (rp, ci, pp, pn)) in enumerate(zip(self.owner_order, self.owner_shards)):
             if q != self.rank:
                 peer.wait([q], cur)
@@ -397,7 +425,7 @@ class PeerHalo:
         self.c_peer_buf = [(ctypes.c_void_p * world)(*self.peer_buf[b]) for b in range(2)]
         # peers that asked for my whole range are served by the copy engines (GNNA_HALO_CE=0: always the push kernel)
         self.dense_mask = 0
-        if os.environ.get("GNNA_HALO_CE", "1") == "1":
+        if os.environ.get("GNNA_HALO_CE", "0") == "1":
             for p in range(world):
                 if sg.dense_to[p]:
                     self.dense_mask |= 1 << p

@@ -46,6 +46,9 @@ def build_parser():
     p.add_argument("--synthetic", type=str, default="", help="look-alike graph name[:scale] instead of a dataset file")
     p.add_argument("--decider", type=str, default="b200", choices=["reference", "b200"],
                    help="auto-mode parameter choice: re-tuned for B200 (default) or the reference's heuristics (param.py:71-120)")
+    p.add_argument("--fused", type=str, choices=["True", "False"], default="False",
+                   help="extension: aggregate -> dense product in one kernel with the product on the tensor cores (tcgen05, bf16 "
+                        "operands) where a layer has that shape: GIN forward, GCN backward; hidden dims 32/64/128 (64/128/256 with bf16 rows)")
     p.add_argument("--cuda_graph", type=str, choices=["True", "False"], default="False",
                    help="extension: capture one training epoch (forward, backward, Adam) in a CUDA graph and replay it; "
                         "for launch-bound graphs (Cora, citeseer) where ~25 launches cost more than their kernels")
@@ -165,7 +168,8 @@ def main(argv=None):
     conv = layers.GCNConv if args.model == "gcn" else layers.GINConv
     dims = ([dataset.num_features, args.hidden, dataset.num_classes] if args.model == "gcn"
             else [dataset.num_features] + [args.hidden] * 4 + [dataset.num_classes])     # GNNA_main.py:142-171
-    convs = torch.nn.ModuleList([conv(a, b, gather_dtype=args.gather_dtype) for a, b in zip(dims[:-1], dims[1:])]).to(device)
+    convs = torch.nn.ModuleList([conv(a, b, gather_dtype=args.gather_dtype, fused=args.fused == "True")
+                                 for a, b in zip(dims[:-1], dims[1:])]).to(device)
     if verbose:
         print(convs)
     use_graph = args.cuda_graph == "True"

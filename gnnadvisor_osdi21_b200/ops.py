@@ -25,7 +25,7 @@ import torch
 from . import _lib
 
 __all__ = ["SAG", "forward", "backward", "forward_gin", "backward_gin", "build_part",
-           "build_part_exact", "aggregate_bf16", "aggregate_gemm_fused", "forward_gin_fused",
+           "build_part_exact", "aggregate_bf16", "aggregate_gemm_fused", "forward_gin_fused", "backward_fused",
            "forward_mixed", "backward_mixed", "forward_gin_mixed", "backward_gin_mixed", "scale_rows_bf16",
            "degrees_from_row_ptr", "launch_info"]
 
@@ -347,6 +347,35 @@ def forward_gin_fused(input, weight, row_pointers, column_index, epsilon, part_p
     behind the aggregation.  Same return as forward_gin: [out, X_agg]; X_agg is exact fp32."""
     return aggregate_gemm_fused(2, input, weight, row_pointers, column_index, None, epsilon, part_pointers, part2Node,
                                 partSize, dimWorker, warpPerBlock)
+
+
+def backward_fused(d_output, X, W, row_pointers, column_index, degrees, part_pointers, part2Node,
+                   partSize, dimWorker, warpPerBlock, gather_bf16=False):
+    """GCN backward with aggregate -> product fused (extension): G = Ahat @ d_output and d_X = G @ W^T in ONE kernel
+    (tcgen05 tile, bf16 operands), d_W = X^T @ G by SGEMM.  Reference: spmm_backward_cuda, kernel.cu:422-476 (aggregation,
+    then two torch::mm).  Returns [d_X, d_W] like backward().  d_output's width must have a fused tile (32/64/128 fp32
+    rows, 64/128/256 bf16 rows) and X's width must be <= 256."""
+    _feat2d(d_output, "d_output")
+    _feat2d(X, "X")
+    _feat2d(W, "W")
+    _check_input(degrees, "degrees", torch.float32)
+    n, dout = d_output.shape
+    din = X.shape[1]
+    if X.shape[0] != n or W.shape[0] != din or W.shape[1] != dout:
+        raise RuntimeError("size mismatch: d_output %s, X %s, W %s" % (tuple(d_output.shape), tuple(X.shape), tuple(W.shape)))
+    # rows travel pre-scaled by n_j (mode 3): fp32 through the pre-scale pass, bf16 through scale_rows_bf16
+    if gather_bf16:
+        rows = scale_rows_bf16(d_output, degrees)
+    else:
+        rows = torch.empty_like(d_output)
+        with torch.cuda.device(X.device):
+            _lib.check(_lib.load().gnna_prescale_rows_f32(_ptr(d_output), _ptr(rows), _ptr(degrees), n, dout, _stream()), "prescale")
+    d_input, g = aggregate_gemm_fused(3, rows, W.t().contiguous(), row_pointers, column_index, degrees, 1.0,
+                                      part_pointers, part2Node, partSize, dimWorker, warpPerBlock)      # kernel.cu:436-472
+    d_weight = torch.empty((din, dout), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().gnna_sgemm_f32(1, 0, din, dout, n, _ptr(X), _ptr(g), _ptr(d_weight), _stream()), "X^T G")   # :473
+    return [d_input, d_weight]
 
 
 # ------------------------------------------------------------------------------------------ build_part

@@ -118,6 +118,18 @@ GNNA_API int gnna_aggregate_part_f32_ex(int mode, int accumulate, const float *X
                                         const int32_t *part2node, int dim, int64_t num_parts,
                                         int part_size, int dim_worker, int warp_per_block, void *stream);
 
+/* The sharded step with the halo exchange FUSED into the aggregation: ONE launch over the concatenation of a rank's
+ * per-owner sub-CSRs (segment s = groups [seg_bounds[s], seg_bounds[s+1]), gathering rows owned by rank seg_peer[s]; -1 =
+ * the rank's own rows).  The CTAs of a peer's segment wait INSIDE the kernel (ld.acquire.sys on that peer's flag in the halo
+ * control block `my_ctrl`, bounded) until the peer's push has delivered this step's rows, while the CTAs ahead of them
+ * aggregate what has already landed: the NVLink transfer overlaps the gather segment by segment with no kernel boundary
+ * in between.  out is zero-filled and accumulated with reductions.  mode 0, 2, 3; dim % 4 == 0.  No reference counterpart. */
+GNNA_API int gnna_aggregate_gated_f32(int mode, const float *X, int64_t num_src_rows, float *out, int64_t num_dst_rows,
+                                      const int32_t *row_ptr, const int32_t *col_idx, const float *degrees, float eps,
+                                      const int32_t *part_ptr, const int32_t *part2node, int dim, int64_t num_parts,
+                                      const int64_t *seg_bounds_host, const int32_t *seg_peer_host, int num_segs,
+                                      void *my_ctrl, int part_size, int dim_worker, int warp_per_block, void *stream);
+
 /* Xs[i,:] = degrees[i] * X[i,:] (X == Xs allowed): the pre-scale pass of the default GCN path, exposed
  * so a producer can hand pre-scaled rows to gnna_aggregate_part_f32_ex(mode 3) / the halo push.          */
 GNNA_API int gnna_prescale_rows_f32(const float *X, float *Xs, const float *degrees, int64_t num_rows, int dim, void *stream);

@@ -61,14 +61,19 @@ def _worker(rank, world, port, ret):
         total = sum(int(s[1].numel()) for s in sg.owner_shards)
         assert total == sg.col_idx.numel() and sg.owner_order[0] == rank
         out = torch.empty(sg.n_local, dim, device=dev)
-        for step in range(1, 6):
-            X = rand_features(n, dim, 700 + step)
-            for mode in (1, 2):
-                sg.write_local(peer, torch.from_numpy(X[v0:v1]).to(dev), prescale=(mode == 1))
-                got = sg.aggregate_overlapped(mode, peer, out).cpu().numpy()
-                ref = oracle.aggregate(mode, X, ci, deg, 0.5, pp, pn)[v0:v1]
-                terms = oracle.aggregate(mode, np.abs(X), ci, deg, 0.5, pp, pn)[v0:v1]
-                assert_close(got, ref, what="overlapped rank %d step %d mode %d" % (rank, step, mode), terms=terms)
+        # GNNA_GATED=1 (default): ONE kernel whose CTAs wait for a peer's flag inside the kernel (exchange fused into the
+        # aggregation); 0: one kernel per owner sub-shard with wait kernels in between
+        for gated in ("1", "0", "1"):
+            os.environ["GNNA_GATED"] = gated
+            for step in range(1, 6):
+                X = rand_features(n, dim, 700 + step)
+                for mode in (1, 2):
+                    sg.write_local(peer, torch.from_numpy(X[v0:v1]).to(dev), prescale=(mode == 1))
+                    out.fill_(float("nan"))
+                    got = sg.aggregate_overlapped(mode, peer, out).cpu().numpy()
+                    ref = oracle.aggregate(mode, X, ci, deg, 0.5, pp, pn)[v0:v1]
+                    terms = oracle.aggregate(mode, np.abs(X), ci, deg, 0.5, pp, pn)[v0:v1]
+                    assert_close(got, ref, what="overlapped (gated=%s) rank %d step %d mode %d" % (gated, rank, step, mode), terms=terms)
         assert peer.error() == 0
         peer.close()
         ret[rank] = "ok"

@@ -580,6 +580,55 @@ def test_fused_tile_edge_cases():
                                  *g.pargs(), 32, 32, 8)
 
 
+@pytest.mark.parametrize("gather_dtype", ["fp32", "bf16"])
+def test_fused_layers_in_the_product_path(gather_dtype):
+    """GINConv / GCNConv(fused=True): the fused tcgen05 tile behind the layer API (forward of GIN, backward of GCN),
+    compared with the unfused layers on the same weights: outputs and gradients agree within the bf16 operand bound
+    (5e-2 of the absolute terms, as test_fused_aggregate_gemm_tcgen05), the aggregated matrices (saved X_agg / G, which feed
+    dW) at the fp32 tolerance for fp32 rows.  A width without a fused tile silently keeps the unfused operators."""
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+    info = type("Info", (), {})()
+    info.row_pointers, info.column_index, info.degrees, info.partPtr, info.part2Node = g.d_rp, g.d_ci, g.d_deg, g.d_pp, g.d_pn
+    info.partSize, info.dimWorker, info.warpPerBlock = 32, 32, 8
+    X = dev(rand_features(g.n, 64, 11) * 0.1)
+    dO = dev(rand_features(g.n, 64, 12))
+
+    def run(layer_cls, fused, din, dout, x):
+        torch.manual_seed(5)
+        layer = layer_cls(din, dout, gather_dtype=gather_dtype, fused=fused).to(DEV)
+        xin = x.clone().requires_grad_(True)
+        out = layer(xin, info)
+        out.backward(dO[:, :dout].contiguous())
+        return out.detach(), xin.grad.detach(), layer.weights.grad.detach()
+
+    for cls, din, dout in ((layers.GINConv, 64, 64), (layers.GCNConv, 64, 64), (layers.GINConv, 64, 41)):
+        o_f, dx_f, dw_f = run(cls, True, din, dout, X)
+        o_u, dx_u, dw_u = run(cls, False, din, dout, X)
+        scale = lambda t: float(t.abs().max())   # noqa: E731
+        assert float((o_f - o_u).abs().max()) <= 5e-2 * scale(o_u), cls.__name__
+        assert float((dx_f - dx_u).abs().max()) <= 5e-2 * scale(dx_u), cls.__name__
+        assert float((dw_f - dw_u).abs().max()) <= 5e-2 * scale(dw_u), cls.__name__
+        assert float((o_f - o_u).abs().max()) > 0 or float((dx_f - dx_u).abs().max()) > 0      # the fused kernel did run
+    # 48-wide aggregated matrix: no fused tile -> identical to the unfused layer
+    X48 = dev(rand_features(g.n, 48, 13) * 0.1)
+    o_f, dx_f, dw_f = run(layers.GINConv, True, 48, 64, X48)
+    o_u, dx_u, dw_u = run(layers.GINConv, False, 48, 64, X48)
+    assert_close(o_f.cpu().numpy(), o_u.cpu().numpy(), what="fallback out")
+
+
+def test_backward_fused_against_oracle():
+    """ops.backward_fused: G = Ahat dOut and dX = G W^T in one kernel, dW = X^T G.  G-dependent outputs against the oracle."""
+    rp, ci = GRAPHS["rmat"]()
+    g = G(rp, ci, 32)
+    X, W, dO = rand_features(g.n, 128, 1), rand_weight(128, 64, 2), rand_features(g.n, 64, 3)
+    dX, dW = ops.backward_fused(dev(dO), dev(X), dev(W), *g.gargs(), g.d_deg, *g.pargs(), 32, 32, 8)
+    odX, odW = oracle.backward(dO, X, W, rp, ci, g.deg, g.pp, g.pn)
+    aG = oracle.closed_form(1, np.abs(dO).astype(np.float64), rp, ci)
+    assert_close(dW.cpu().numpy(), odW, what="dW (fp32 G)", terms=np.abs(X.T).astype(np.float64) @ aG)
+    assert_close(dX.cpu().numpy(), odX, rtol=5e-2, what="dX (bf16 tile)", terms=aG @ np.abs(W.T))
+
+
 # ------------------------------------------------------------------------------------------ split CSRs, host pipeline
 def test_aggregation_over_split_csrs_accumulates():
     """gnna_aggregate_part_f32_ex: the edges of a graph split over two CSRs (by column range, as the sharded

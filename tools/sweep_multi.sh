@@ -1,6 +1,6 @@
 #!/bin/bash
 # Multi-GPU A/B of the halo exchange and the partition cost model on the visible GPUs (bench.py --no-extras lines):
-#   copy-engine dense exchange on/off  x  row weights.   gpurun --gpus 4 -- bash tools/sweep_multi.sh
+#   fused exchange+aggregation kernel (gated) vs per-owner sub-kernels, copy-engine exchange, push CTAs, row weights.   gpurun --gpus 4 -- bash tools/sweep_multi.sh
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -24,8 +24,13 @@ except Exception as e:
 PY
   tail -3 "gpurun_out/sweep_${NG}gpu_${name}.err" | grep -v "OMP_NUM\|^\*\*\*\|NCCL version" | head -3
 }
-run ce_w0 GNNA_ROW_WEIGHT=0
-run ce_w40 GNNA_ROW_WEIGHT=$((10 * (NG - 1)))
-run ce_w160 GNNA_ROW_WEIGHT=$((40 * (NG - 1)))
-run kernelpush_w160 GNNA_HALO_CE=0 GNNA_DENSE_HALO=0 GNNA_ROW_WEIGHT=$((40 * (NG - 1)))
-run kernelpush_w0 GNNA_HALO_CE=0 GNNA_DENSE_HALO=0 GNNA_ROW_WEIGHT=0
+W1=$((10 * (NG - 1))); W4=$((40 * (NG - 1)))
+run gated_w0 GNNA_ROW_WEIGHT=0
+run gated_w$W1 GNNA_ROW_WEIGHT=$W1
+run gated_w$W4 GNNA_ROW_WEIGHT=$W4
+run gated_w0_ops64 GNNA_ROW_WEIGHT=0 GNNA_OWNER_PS=64
+run gated_w0_ctas192 GNNA_ROW_WEIGHT=0 GNNA_PUSH_CTAS=192
+run gated_w0_ctas48 GNNA_ROW_WEIGHT=0 GNNA_PUSH_CTAS=48
+run gated_ce_w0 GNNA_ROW_WEIGHT=0 GNNA_HALO_CE=1
+run subkernels_w$W4 GNNA_GATED=0 GNNA_ROW_WEIGHT=$W4
+run subkernels_w0 GNNA_GATED=0 GNNA_ROW_WEIGHT=0
