@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-fvisibility=hidden",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-fvisibility=hidden,-fopenmp",
     "--threads", "4",
 ]
 
@@ -65,7 +65,7 @@ def build_lib(force=False, verbose=False, defines=(), out=None):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [_nvcc(), "-shared", "-o", target] + objs + [
         "-gencode", "arch=compute_100a,code=sm_100a",
-        "-lcublas", "-Xlinker", "-rpath,/usr/local/cuda/lib64",
+        "-lcublas", "-lgomp", "-Xlinker", "-rpath,/usr/local/cuda/lib64",
     ]
     subprocess.run(link, check=True, env=env)
     for o in objs:

@@ -124,30 +124,6 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
 {
     // dim = row stride of `out` (% VEC == 0, 16-byte aligned rows); ldx = row stride of X in elements (>= dim)
     constexpr int S = 32 / LPR;                      // neighbour-groups per warp
-    // Sharded path, exchange fused into the aggregation (common.h: GateParams): the rows of a peer are still crossing
-    // NVLink when this kernel starts.  A CTA whose groups gather a peer's rows waits for that peer's flag -- set by the
-    // peer's push after its last remote store (release, system scope) -- before it touches them; CTAs are dispatched in
-    // group order and the segments are ordered by arrival, so the SMs aggregate what is there while the rest lands.
-    if (gate.nseg > 0) {
-        if (threadIdx.x == 0) {
-            const long long per_cta = (long long)(blockDim.x >> 5) * S;
-            const long long g0 = (long long)blockIdx.x * per_cta;
-            const long long g1 = g0 + per_cta < num_parts ? g0 + per_cta : num_parts;
-            const unsigned step = *reinterpret_cast<const volatile unsigned *>(gate.step_ptr);
-            for (int sgm = 0; sgm < gate.nseg; sgm++) {
-                if (gate.peer[sgm] < 0 || g0 >= gate.bounds[sgm + 1] || g1 <= gate.bounds[sgm]) continue;
-                const unsigned *f = gate.flags + gate.peer[sgm];
-                unsigned v;
-                const long long t0 = clock64();
-                do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                    if (v >= step) break;
-                    if (clock64() - t0 > 8000000000LL) { atomicExch(gate.error_word, 2u); break; }
-                } while (true);
-            }
-        }
-        __syncthreads();
-    }
     // neighbour ids fetched per lane per batch: 32 neighbours per batch (8 at most per lane); the exact-GCN
     // variant also carries a weight per id and keeps the short batch (it is about rounding, not speed)
     constexpr int IPL_SHORT = (LPR >= 8) ? 1 : 8 / LPR;
@@ -172,6 +148,34 @@ aggregate_kernel(const T *__restrict__ X, float *__restrict__ out,
         src = ldg_stream(part2node + g);
         beg = ldg_stream(part_ptr + g);
         end = ldg_stream(part_ptr + g + 1);
+    }
+    // Sharded path, exchange fused into the aggregation (common.h: GateParams): the rows of a peer are still crossing
+    // NVLink when this kernel starts.  A CTA whose groups gather a peer's rows waits for that peer's flag -- set by the
+    // peer's push after its last remote store (release, system scope) -- before it touches them; CTAs are dispatched in
+    // group order and the segments are ordered by arrival, so the SMs aggregate what is there while the rest lands.
+    // The wait sits HERE, after the table entries of the group were requested (they are this rank's own static data), so
+    // its round trip overlaps theirs; CTAs of the rank's own segment skip it without touching memory.
+    if (gate.nseg > 0) {
+        const long long per_cta = (long long)(blockDim.x >> 5) * S;
+        const long long g0 = (long long)blockIdx.x * per_cta;
+        const long long g1 = g0 + per_cta < num_parts ? g0 + per_cta : num_parts;
+        bool need = false;
+        for (int sgm = 0; sgm < gate.nseg; sgm++)
+            need |= gate.peer[sgm] >= 0 && g0 < gate.bounds[sgm + 1] && g1 > gate.bounds[sgm];
+        if (need) {                                  // CTA-uniform
+            if (threadIdx.x == 0) {
+                const unsigned step = *reinterpret_cast<const volatile unsigned *>(gate.step_ptr);
+                for (int sgm = 0; sgm < gate.nseg; sgm++) {
+                    if (gate.peer[sgm] < 0 || g0 >= gate.bounds[sgm + 1] || g1 <= gate.bounds[sgm]) continue;
+                    const volatile unsigned *f = gate.flags + gate.peer[sgm];
+                    const long long t0 = clock64();
+                    while (*f < step)                // relaxed polling; the acquire that orders the row loads follows
+                        if (clock64() - t0 > 8000000000LL) { atomicExch(gate.error_word, 2u); break; }
+                }
+                asm volatile("fence.acquire.sys;" ::: "memory");
+            }
+            __syncthreads();
+        }
     }
     const int len = max(end - beg, 0);               // end <= beg: empty group, contributes nothing
     const int maxlen = __reduce_max_sync(FULL, len); // warp-uniform trip count

@@ -16,6 +16,7 @@
 // checked: the result is a permutation, applied consistently, and it shortens the average edge span
 // of graphs with community structure (tests/test_reorder.py).
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cstdint>
 #include <numeric>
 #include <utility>
@@ -90,16 +91,25 @@ extern "C" int gnna_rabbit_reorder_host(const int32_t *src, const int32_t *dst, 
     const int32_t n = (int32_t)num_nodes;
 
     // 1. symmetric weighted adjacency, no self loops, duplicates merged
-    std::vector<uint64_t> keys;
-    keys.reserve((size_t)num_edges * 2);
+    // (the edge list passes are the bulk of the time at 10^8 edges: all host threads, as the reference's OpenMP build)
+    std::vector<uint64_t> keys((size_t)num_edges * 2);
+    long long bad = -1;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < num_edges; i++) {
         const int32_t a = src[i], b = dst[i];
-        GNNA_REQUIRE(a >= 0 && a < n && b >= 0 && b < n, "rabbit_reorder: vertex id out of range at edge %lld", (long long)i);
-        if (a == b) continue;
-        keys.push_back(((uint64_t)(uint32_t)a << 32) | (uint32_t)b);
-        keys.push_back(((uint64_t)(uint32_t)b << 32) | (uint32_t)a);
+        if (a < 0 || a >= n || b < 0 || b >= n) {
+#pragma omp critical
+            if (bad < 0 || i < bad) bad = i;
+            keys[2 * i] = keys[2 * i + 1] = ~0ull;
+            continue;
+        }
+        if (a == b) { keys[2 * i] = keys[2 * i + 1] = ~0ull; continue; }     // self loop: dropped below
+        keys[2 * i] = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
+        keys[2 * i + 1] = ((uint64_t)(uint32_t)b << 32) | (uint32_t)a;
     }
-    std::sort(keys.begin(), keys.end());
+    GNNA_REQUIRE(bad < 0, "rabbit_reorder: vertex id out of range at edge %lld", bad);
+    __gnu_parallel::sort(keys.begin(), keys.end());
+    while (!keys.empty() && keys.back() == ~0ull) keys.pop_back();
     Dendrogram g;
     g.es.resize(n);
     g.com.resize(n);
@@ -123,8 +133,8 @@ extern "C" int gnna_rabbit_reorder_host(const int32_t *src, const int32_t *dst, 
     // 2. incremental aggregation in ascending (unweighted) degree order
     std::vector<int32_t> order(n);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int32_t a, int32_t b) { return g.es[a].size() < g.es[b].size(); });
+    __gnu_parallel::stable_sort(order.begin(), order.end(),
+                                [&](int32_t a, int32_t b) { return g.es[a].size() < g.es[b].size(); });
     std::vector<int32_t> tops;
     std::vector<WEdge> buf;
     for (int32_t v : order) {

@@ -293,7 +293,8 @@ class ShardedGraph:
                                                     p(self.gated_col), p(self.degrees_ext) if kmode == 3 else ctypes.c_void_p(0),
                                                     float(eps), p(self.gated_pp), p(self.gated_pn), d, self.gated_pn.numel(),
                                                     self.gated_bounds, self.gated_peer, self.world, ctypes.c_void_p(peer.ctrl_ptr),
-                                                    self.part_size, int(dim_worker), int(warp_per_block), st), "gated aggregate")
+                                                    self.part_size, int(dim_worker),
+                                                    int(os.environ.get("GNNA_GATED_WPB", warp_per_block)), st), "gated aggregate")
             peer.ack()
             cur.wait_event(self._ev_pushed)
             return out

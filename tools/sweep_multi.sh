@@ -25,12 +25,12 @@ PY
   tail -3 "gpurun_out/sweep_${NG}gpu_${name}.err" | grep -v "OMP_NUM\|^\*\*\*\|NCCL version" | head -3
 }
 W1=$((10 * (NG - 1))); W4=$((40 * (NG - 1)))
-run gated_w0 GNNA_ROW_WEIGHT=0
-run gated_w$W1 GNNA_ROW_WEIGHT=$W1
-run gated_w$W4 GNNA_ROW_WEIGHT=$W4
-run gated_w0_ops64 GNNA_ROW_WEIGHT=0 GNNA_OWNER_PS=64
-run gated_w0_ctas192 GNNA_ROW_WEIGHT=0 GNNA_PUSH_CTAS=192
-run gated_w0_ctas48 GNNA_ROW_WEIGHT=0 GNNA_PUSH_CTAS=48
-run gated_ce_w0 GNNA_ROW_WEIGHT=0 GNNA_HALO_CE=1
-run subkernels_w$W4 GNNA_GATED=0 GNNA_ROW_WEIGHT=$W4
 run subkernels_w0 GNNA_GATED=0 GNNA_ROW_WEIGHT=0
+run subkernels_w$W1 GNNA_GATED=0 GNNA_ROW_WEIGHT=$W1
+run subkernels_w$W4 GNNA_GATED=0 GNNA_ROW_WEIGHT=$W4
+run gated_w0 GNNA_ROW_WEIGHT=0
+run gated_w0_wpb16 GNNA_ROW_WEIGHT=0 GNNA_GATED_WPB=16
+run gated_w$W1 GNNA_ROW_WEIGHT=$W1
+run subkernels_w0_ops64 GNNA_GATED=0 GNNA_ROW_WEIGHT=0 GNNA_OWNER_PS=64
+run gated_ce_w0 GNNA_ROW_WEIGHT=0 GNNA_HALO_CE=1
+run subkernels_w0_ctas192 GNNA_GATED=0 GNNA_ROW_WEIGHT=0 GNNA_PUSH_CTAS=192
