@@ -79,7 +79,7 @@ def l2_peak_gbs(device=None):
     if device.index in _L2_PEAK:
         return _L2_PEAK[device.index]
     lib = _lib.load()
-    nbytes, passes = 40 << 20, 40
+    nbytes, passes = 30 << 20, 80
     with torch.cuda.device(device):
         buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
         sink = torch.zeros(1, dtype=torch.int32, device=device)
@@ -88,7 +88,7 @@ def l2_peak_gbs(device=None):
             per_pass = ctypes.c_int64(0)
 
             def run():
-                _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), nbytes, passes, mode, 2, ctypes.c_void_p(sink.data_ptr()),
+                _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), nbytes, passes, mode, 3, ctypes.c_void_p(sink.data_ptr()),
                                                   ctypes.byref(per_pass), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2 probe")
             best = min(timed(run, 1, 1) for _ in range(5))
             res[name + "_GBs"] = per_pass.value * passes / (best * 1e-3) / 1e9

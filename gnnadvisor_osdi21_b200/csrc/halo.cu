@@ -38,6 +38,7 @@ struct HaloPushParams {
     unsigned *error_word;                 // local: set to non-zero when a wait timed out
     int slots, dim;
     unsigned skip_mask;                   // slots (bit s) served by the copy engines (gnna_halo_push_ce): not this kernel's
+    int interleave;                       // 1: CTA c starts at slot c % slots, so all peers are fed at once (see the kernel)
     const unsigned *step_ptr;             // local control word holding the current step (1, 2, 3, ...): read on the
                                           // device so that a captured CUDA graph can be replayed step after step
 };
@@ -62,7 +63,13 @@ halo_push_kernel(const float *__restrict__ x_local, const long long *__restrict_
     __shared__ int s_ok;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned step = *reinterpret_cast<const volatile unsigned *>(prm.step_ptr);
-    for (int p = 0; p < prm.slots; p++) {                    // slot
+    // One stream of remote stores to ONE peer runs at 270-375 GB/s (measured, 2/4/8xB200) while a GPU's NVLink egress is
+    // 900 GB/s to all peers together.  interleave = 1 (default, GNNA_PUSH_INTERLEAVE): the CTAs start at different slots and
+    // walk the ring from there, so every peer is being written at any moment; 0: all CTAs serve slot 0, then slot 1, ...
+    // (blocks arrive one after the other, the first one sooner).
+    const int first = prm.interleave ? (int)(blockIdx.x % (unsigned)prm.slots) : 0;
+    for (int pi = 0; pi < prm.slots; pi++) {                 // slot
+        const int p = (pi + first) % prm.slots;
         if ((prm.skip_mask >> p) & 1u) continue;
         // the buffer of this parity was last read by this peer at step-2: wait for its acknowledgement
         if (threadIdx.x == 0) {
@@ -201,6 +208,16 @@ __global__ void halo_raise_flag_kernel(unsigned *peer_flag, const unsigned *step
     st_release_sys(peer_flag, *reinterpret_cast<const volatile unsigned *>(step_ptr));
 }
 
+static int push_interleave()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("GNNA_PUSH_INTERLEAVE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 // first kernel of a step on the compute stream: step += 1 (everything else of the step is ordered after it)
 __global__ void halo_bump_kernel(unsigned *step_ptr) { *step_ptr = *step_ptr + 1; }
 
@@ -286,6 +303,7 @@ extern "C" int gnna_halo_push_f32(const float *x_local, const int64_t *send_idx,
     prm.slots = world - 1;
     prm.dim = dim;
     prm.step_ptr = ctrl + 49;
+    prm.interleave = push_interleave();
     halo_push_kernel<<<ctas, PUSH_WARPS * 32, 0, (cudaStream_t)stream>>>(x_local, (const long long *)send_idx, prm);
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
@@ -339,15 +357,45 @@ extern "C" int gnna_halo_push_ce(const float *x_local, int64_t n_local, const in
     halo_wait_acks_kernel<<<1, 32, 0, st>>>(ce);
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
+    // One point-to-point copy runs at ~270 GB/s (measured, 8xB200: 7.5 MB blocks); NVLink gives a GPU 900 GB/s of egress to
+    // ALL its peers together.  The copies therefore run CONCURRENTLY, one side stream per peer, forked from and joined back
+    // into the caller's stream with events (a pattern a stream capture records as parallel branches of the graph).
+    // GNNA_CE_STREAMS=0: one after the other on the caller's stream (ring order).
+    static int ce_parallel = -1;
+    if (ce_parallel < 0) {
+        const char *e = getenv("GNNA_CE_STREAMS");
+        ce_parallel = (e && e[0] == '0') ? 0 : 1;
+    }
+    static cudaStream_t side[64][MAX_PEERS];
+    static cudaEvent_t ev_fork[64], ev_join[64][MAX_PEERS];
+    static bool side_ready[64] = {false};
+    int dev = 0;
+    GNNA_CUDA_CHECK(cudaGetDevice(&dev));
+    GNNA_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    if (ce_parallel && !side_ready[dev]) {
+        GNNA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+        for (int i = 0; i < MAX_PEERS; i++) {
+            GNNA_CUDA_CHECK(cudaStreamCreateWithFlags(&side[dev][i], cudaStreamNonBlocking));
+            GNNA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[dev][i], cudaEventDisableTiming));
+        }
+        side_ready[dev] = true;
+    }
     const size_t bytes = (size_t)n_local * (size_t)dim * sizeof(float);
-    for (int sl = 0; sl < world - 1; sl++) {                     // ring order: every receiver sees its blocks arrive in turn
+    if (ce_parallel) GNNA_CUDA_CHECK(cudaEventRecord(ev_fork[dev], st));
+    for (int sl = 0; sl < world - 1; sl++) {                     // ring order (of issue, when the copies run concurrently)
         if (!((prm.skip_mask >> sl) & 1u)) continue;
+        cudaStream_t cs = ce_parallel ? side[dev][sl] : st;
+        if (ce_parallel) GNNA_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_fork[dev], 0));
         if (bytes)
             GNNA_CUDA_CHECK(cudaMemcpyAsync(prm.peer_base[sl] + prm.dst_row0[sl] * (long long)dim, x_local, bytes,
-                                            cudaMemcpyDeviceToDevice, st));
-        halo_raise_flag_kernel<<<1, 1, 0, st>>>(prm.peer_flag[sl], ctrl + 49);
+                                            cudaMemcpyDeviceToDevice, cs));
+        halo_raise_flag_kernel<<<1, 1, 0, cs>>>(prm.peer_flag[sl], ctrl + 49);
         GNNA_CUDA_CHECK(cudaGetLastError());
         count_launch(1);
+        if (ce_parallel) {
+            GNNA_CUDA_CHECK(cudaEventRecord(ev_join[dev][sl], cs));
+            GNNA_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join[dev][sl], 0));
+        }
     }
     if (sparse > 0) {
         GNNA_REQUIRE(send_idx || max_chunks == 0, "halo_push_ce: null send_idx");
@@ -360,6 +408,7 @@ extern "C" int gnna_halo_push_ce(const float *x_local, int64_t n_local, const in
         prm.slots = world - 1;
         prm.dim = dim;
         prm.step_ptr = ctrl + 49;
+        prm.interleave = push_interleave();
         halo_push_kernel<<<ctas, PUSH_WARPS * 32, 0, st>>>(x_local, (const long long *)send_idx, prm);
         GNNA_CUDA_CHECK(cudaGetLastError());
         count_launch(1);

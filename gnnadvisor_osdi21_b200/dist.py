@@ -30,12 +30,12 @@ def default_row_weight(world, avg_degree=None):
     (proportional to its edges) plus halo traffic.  When the halo rows are gathered and pushed by a kernel (sparse halos)
     every row a rank owns costs its SMs time once per peer that needs it -- measured on 8xB200 (D=64): 0.0154 ns per edge
     against ~4 ns per row at 7 peers, i.e. ~40 edge-equivalents per row and peer.  On DENSE graphs (avg_degree / world >= 16:
-    every peer needs nearly every row, the blocks travel on the copy engines, csrc/halo.cu) rows cost the SMs nothing and
-    the cut balances edges alone."""
+    every peer needs nearly every row) that weight shifts so many edges onto the hub ranks that their kernel becomes the
+    step (0.24 vs 0.20 ms at 8 GPUs); a quarter of it is the measured optimum there."""
     if world <= 1:
         return 0
     if avg_degree is not None and avg_degree / world >= 16:
-        return 0
+        return 10 * (world - 1)          # measured at 4 and 8 GPUs (profiles/r02_*sweep*): 10 beats both 0 and 40 per peer
     return 40 * (world - 1)
 
 

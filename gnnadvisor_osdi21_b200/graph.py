@@ -76,6 +76,8 @@ def stream_pairs(num_nodes, start, count, kind="rmat", seed=20211, device="cpu",
     """Pairs [start, start+count) of the directed pair stream of graph (num_nodes, kind, seed): (src, dst) int64
     tensors with self loops and out-of-range ids already dropped (so fewer than `count` come back)."""
     N = int(num_nodes)
+    if torch.device(device).type == "cuda" and os.environ.get("GNNA_GRAPHGEN_KERNEL", "1") == "1":
+        return _stream_pairs_cuda(N, int(start), int(count), kind, int(seed), torch.device(device), rmat)
     idx = torch.arange(int(start), int(start) + int(count), dtype=torch.int64, device=device)
     base = _mix64(idx ^ _s64(int(seed) * _GOLD + 0x1234567))
     if kind == "uniform":
@@ -109,6 +111,24 @@ def stream_features(ids, dim, seed=20212):
     h = _mix64(_mix64(ids ^ _s64(int(seed) * _GOLD + 0x7654321)) + cols * _s64(_GOLD))
     u = ((h >> 40) & 0xFFFFFF).to(torch.float32)                 # 24 bits: exact in float32
     return (u * (2.0 ** -23) - 1.0) * 1.7320508
+
+
+def _stream_pairs_cuda(N, start, count, kind, seed, device, rmat):
+    """stream_pairs as ONE kernel of libgnna_b200.so (csrc/graphgen.cu): the same pairs, bit for bit."""
+    import ctypes
+    from . import _lib
+    a, b, c, _ = rmat
+    bits = max(1, math.ceil(math.log2(max(N, 2))))
+    src = torch.empty(count, dtype=torch.int64, device=device)
+    dst = torch.empty(count, dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().gnna_stream_pairs(
+            start, count, (int(seed) * _GOLD + 0x1234567) & _M64, N, 1 if kind == "uniform" else 0, bits,
+            int(a * 2 ** 32), int((a + b) * 2 ** 32), int((a + b + c) * 2 ** 32),
+            ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "stream_pairs")
+    keep = src >= 0
+    return src[keep], dst[keep]
 
 
 def synth_graph(num_nodes, num_edges, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT, exact=True):

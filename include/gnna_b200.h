@@ -307,6 +307,13 @@ typedef struct gnna_launch_info {
 GNNA_API int gnna_query_launch(int elem_bytes, int dim, int64_t num_parts, int dim_worker, int warp_per_block,
                       gnna_launch_info *info);
 
+/* Workload generation: pairs [start, start+count) of the counter-based pair stream that defines the synthetic look-alike
+ * graphs (gnnadvisor_osdi21_b200/graph.py: stream_pairs -- splitmix64 of the pair index, R-MAT (kind 0, thresholds scaled by
+ * 2^32, `bits` levels) or uniform (kind 1)); dropped pairs (self loops, ids >= num_nodes) come back as -1/-1.  Bit for bit what
+ * the torch definition gives on the CPU, as one kernel.  No reference counterpart (the reference reads dataset files).   */
+GNNA_API int gnna_stream_pairs(int64_t start, int64_t count, uint64_t seed_mix, int64_t num_nodes, int kind, int bits,
+                               uint64_t t_a, uint64_t t_ab, uint64_t t_abc, int64_t *src_out, int64_t *dst_out, void *stream);
+
 /* Measurement infrastructure: read `bytes` of `buf` (a buffer that fits in L2) `passes` times with 128-bit loads that
  * bypass L1 -- mode 0 a coalesced stream, mode 1 randomly ordered 256-byte rows (the D=64 fp32 gather's pattern).  Timed
  * by the caller with CUDA events, it gives bench.py the L2 -> SM bandwidth of the box: the roof of the aggregation when

@@ -118,4 +118,4 @@ def test_partition_ranges_balance_edges_not_nodes():
     rows_e = [v[i + 1] - v[i] for i in range(4)]
     rows_w = [w[i + 1] - w[i] for i in range(4)]
     assert max(rows_w) < max(rows_e) and gdist.default_row_weight(1) == 0 and gdist.default_row_weight(8) == 280
-    assert gdist.default_row_weight(8, avg_degree=492) == 0 and gdist.default_row_weight(8, avg_degree=14.5) == 280
+    assert gdist.default_row_weight(8, avg_degree=492) == 70 and gdist.default_row_weight(8, avg_degree=14.5) == 280

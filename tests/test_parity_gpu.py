@@ -784,6 +784,19 @@ def test_run_based_kernel_auto_rule_on_a_dense_graph():
     assert_close(y.cpu().numpy(), ref, rtol=1e-2, what="auto mixed forward", terms=4 * terms)
 
 
+@pytest.mark.parametrize("kind,n", [("rmat", 232965), ("rmat", 111059956), ("uniform", 3327), ("rmat", 2)])
+def test_pair_stream_kernel_equals_the_torch_definition(kind, n):
+    """csrc/graphgen.cu against graph.stream_pairs' torch integer ops on the CPU: the same pairs bit for bit, so a graph is
+    the same graph wherever it is generated (the reference arm builds it on the host, the ranks shard by shard on GPUs)."""
+    for start, count in ((0, 100000), (123456789012, 50000)):
+        cs, cd = graph.stream_pairs(n, start, count, kind=kind, seed=20211, device="cpu")
+        gs, gd = graph.stream_pairs(n, start, count, kind=kind, seed=20211, device=DEV)
+        assert torch.equal(gs.cpu(), cs) and torch.equal(gd.cpu(), cd) and (cs.numel() > 0 or n == 2)
+    rp_c, ci_c = graph.synth_graph(5000, 160000, kind=kind, seed=9)
+    rp_g, ci_g = graph.synth_graph(5000, 160000, kind=kind, seed=9, device=DEV)
+    assert torch.equal(rp_g.cpu(), rp_c) and torch.equal(ci_g.cpu(), ci_c)
+
+
 # ------------------------------------------------------------------------------------------ single-launch path (small graphs)
 def _launches(fn):
     from gnnadvisor_osdi21_b200 import _lib

@@ -44,11 +44,11 @@ cdeg = ops.degrees_from_row_ptr(c["row_ptr"])
 Xc = torch.randn(c["num_nodes"], 16, device=dev)
 ops.forward(Xc, torch.eye(16, device=dev), c["row_ptr"], c["col_idx"], cdeg, cpp, cpn, 32, 16, 8)   # aggregate_small_kernel
 # the L2 probe (bench.py's roof)
-buf = torch.zeros(40 << 18, device=dev)
+buf = torch.zeros(30 << 18, device=dev)
 sink = torch.zeros(1, dtype=torch.int32, device=dev)
 per = ctypes.c_int64(0)
 for mode in (0, 0, 1):
-    _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), 40 << 20, 4, mode, 2, ctypes.c_void_p(sink.data_ptr()),
+    _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), 30 << 20, 8, mode, 3, ctypes.c_void_p(sink.data_ptr()),
                                       ctypes.byref(per), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "probe")
 torch.cuda.synchronize()
 print("done", wl, D)

@@ -24,13 +24,8 @@ except Exception as e:
 PY
   tail -3 "gpurun_out/sweep_${NG}gpu_${name}.err" | grep -v "OMP_NUM\|^\*\*\*\|NCCL version" | head -3
 }
-W1=$((10 * (NG - 1))); W4=$((40 * (NG - 1)))
-run subkernels_w0 GNNA_GATED=0 GNNA_ROW_WEIGHT=0
-run subkernels_w$W1 GNNA_GATED=0 GNNA_ROW_WEIGHT=$W1
-run subkernels_w$W4 GNNA_GATED=0 GNNA_ROW_WEIGHT=$W4
-run gated_w0 GNNA_ROW_WEIGHT=0
-run gated_w0_wpb16 GNNA_ROW_WEIGHT=0 GNNA_GATED_WPB=16
-run gated_w$W1 GNNA_ROW_WEIGHT=$W1
-run subkernels_w0_ops64 GNNA_GATED=0 GNNA_ROW_WEIGHT=0 GNNA_OWNER_PS=64
-run gated_ce_w0 GNNA_ROW_WEIGHT=0 GNNA_HALO_CE=1
-run subkernels_w0_ctas192 GNNA_GATED=0 GNNA_ROW_WEIGHT=0 GNNA_PUSH_CTAS=192
+run push_interleaved
+run push_ring GNNA_PUSH_INTERLEAVE=0
+run ce_parallel GNNA_HALO_CE=1
+run ce_serial GNNA_HALO_CE=1 GNNA_CE_STREAMS=0
+run push_interleaved_subkernels GNNA_GATED=0
