@@ -87,6 +87,7 @@ SIGNATURES = {
     "gnna_probe_l2_read": (i32, [ctypes.c_void_p, i64, i32, i32, i32, ctypes.c_void_p, ctypes.POINTER(i64), ctypes.c_void_p]),
     "gnna_launch_count": (i64, [i32]),
     "gnna_set_gcn_exact": (i32, [i32]),
+    "gnna_set_tc_gemm": (i32, [i32]),
     "gnna_set_small_parts": (i64, [i64]),
     "gnna_set_staged": (i32, [i32]),
     "gnna_set_runs": (i32, [i32]),
@@ -127,6 +128,12 @@ def launch_count(reset=False):
 def set_gcn_exact(on):
     """True: per-edge rounding of the reference (bit-identical single-group rows); False: pre-scaled (default)."""
     return bool(load().gnna_set_gcn_exact(1 if on else 0))
+
+
+def set_tc_gemm(on):
+    """True (default): the tall-skinny products of a layer run on the tensor cores (tcgen05 kind::tf32, 3xTF32 split);
+    False: every product is a cuBLAS SGEMM.  Returns the previous setting."""
+    return bool(load().gnna_set_tc_gemm(1 if on else 0))
 
 
 def set_small_parts(limit):

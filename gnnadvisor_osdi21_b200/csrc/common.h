@@ -69,6 +69,13 @@ int aggregate_small(int mode, const float *X, float *out, const int32_t *col_idx
 
 bool gcn_exact_mode();   // GNNA_GCN_EXACT / gnna_set_gcn_exact
 
+// Tall-skinny dense products on the tensor cores (gemm_tf32x3.cu: tcgen05 kind::tf32, 3xTF32 split, fp32-grade accuracy).
+// Row-major C[m,n] = op(A) * B; GNNA_ERR_UNSUPPORTED when the shape is not one of the two contractions it is built for (the
+// caller then uses cuBLAS).  row_scale (non-transposed A only, may be null): C[i,:] *= row_scale[i] in the epilogue.
+int gemm_tf32x3(cudaStream_t st, bool ta, bool tb, int64_t m, int64_t n, int64_t k, const float *A, const float *B, float *C,
+                const float *row_scale);
+bool tc_gemm_enabled();  // GNNA_TC_GEMM / gnna_set_tc_gemm (default on)
+
 // Xs[i,:] = degrees[i] * X[i,:]  (X == Xs allowed)
 int prescale_rows(const float *X, float *Xs, const float *degrees, int64_t num_nodes, int dim, cudaStream_t stream);
 

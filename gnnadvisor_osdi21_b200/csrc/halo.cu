@@ -63,10 +63,10 @@ halo_push_kernel(const float *__restrict__ x_local, const long long *__restrict_
     __shared__ int s_ok;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned step = *reinterpret_cast<const volatile unsigned *>(prm.step_ptr);
-    // One stream of remote stores to ONE peer runs at 270-375 GB/s (measured, 2/4/8xB200) while a GPU's NVLink egress is
-    // 900 GB/s to all peers together.  interleave = 1 (default, GNNA_PUSH_INTERLEAVE): the CTAs start at different slots and
-    // walk the ring from there, so every peer is being written at any moment; 0: all CTAs serve slot 0, then slot 1, ...
-    // (blocks arrive one after the other, the first one sooner).
+    // interleave = 0 (default): all CTAs serve slot 0, then slot 1, ... -- blocks arrive one after the other, the first one
+    // soonest, which is what the consumer's segment-by-segment aggregation wants.  1 (GNNA_PUSH_INTERLEAVE=1): the CTAs start
+    // at different slots and walk the ring from there, so every peer is written at any moment; measured on 4xB200 the whole
+    // exchange is then 5 % shorter (0.130 vs 0.136 ms) and the overlapped step no faster (profiles/r02_v4_sweep_4gpu.txt).
     const int first = prm.interleave ? (int)(blockIdx.x % (unsigned)prm.slots) : 0;
     for (int pi = 0; pi < prm.slots; pi++) {                 // slot
         const int p = (pi + first) % prm.slots;
@@ -213,7 +213,7 @@ static int push_interleave()
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("GNNA_PUSH_INTERLEAVE");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;
     }
     return v;
 }
@@ -357,45 +357,18 @@ extern "C" int gnna_halo_push_ce(const float *x_local, int64_t n_local, const in
     halo_wait_acks_kernel<<<1, 32, 0, st>>>(ce);
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
-    // One point-to-point copy runs at ~270 GB/s (measured, 8xB200: 7.5 MB blocks); NVLink gives a GPU 900 GB/s of egress to
-    // ALL its peers together.  The copies therefore run CONCURRENTLY, one side stream per peer, forked from and joined back
-    // into the caller's stream with events (a pattern a stream capture records as parallel branches of the graph).
-    // GNNA_CE_STREAMS=0: one after the other on the caller's stream (ring order).
-    static int ce_parallel = -1;
-    if (ce_parallel < 0) {
-        const char *e = getenv("GNNA_CE_STREAMS");
-        ce_parallel = (e && e[0] == '0') ? 0 : 1;
-    }
-    static cudaStream_t side[64][MAX_PEERS];
-    static cudaEvent_t ev_fork[64], ev_join[64][MAX_PEERS];
-    static bool side_ready[64] = {false};
-    int dev = 0;
-    GNNA_CUDA_CHECK(cudaGetDevice(&dev));
-    GNNA_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
-    if (ce_parallel && !side_ready[dev]) {
-        GNNA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
-        for (int i = 0; i < MAX_PEERS; i++) {
-            GNNA_CUDA_CHECK(cudaStreamCreateWithFlags(&side[dev][i], cudaStreamNonBlocking));
-            GNNA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[dev][i], cudaEventDisableTiming));
-        }
-        side_ready[dev] = true;
-    }
+    // One point-to-point copy of a 7.5-15 MB block runs at ~270 GB/s (measured on 4 and 8 B200s); the copies are issued one
+    // after the other on the caller's stream, in ring order, so every receiver sees its blocks arrive in turn.  (Running
+    // them concurrently on side streams forked inside a stream capture hung the 4-GPU bench in round 2 and was removed.)
     const size_t bytes = (size_t)n_local * (size_t)dim * sizeof(float);
-    if (ce_parallel) GNNA_CUDA_CHECK(cudaEventRecord(ev_fork[dev], st));
-    for (int sl = 0; sl < world - 1; sl++) {                     // ring order (of issue, when the copies run concurrently)
+    for (int sl = 0; sl < world - 1; sl++) {
         if (!((prm.skip_mask >> sl) & 1u)) continue;
-        cudaStream_t cs = ce_parallel ? side[dev][sl] : st;
-        if (ce_parallel) GNNA_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_fork[dev], 0));
         if (bytes)
             GNNA_CUDA_CHECK(cudaMemcpyAsync(prm.peer_base[sl] + prm.dst_row0[sl] * (long long)dim, x_local, bytes,
-                                            cudaMemcpyDeviceToDevice, cs));
-        halo_raise_flag_kernel<<<1, 1, 0, cs>>>(prm.peer_flag[sl], ctrl + 49);
+                                            cudaMemcpyDeviceToDevice, st));
+        halo_raise_flag_kernel<<<1, 1, 0, st>>>(prm.peer_flag[sl], ctrl + 49);
         GNNA_CUDA_CHECK(cudaGetLastError());
         count_launch(1);
-        if (ce_parallel) {
-            GNNA_CUDA_CHECK(cudaEventRecord(ev_join[dev][sl], cs));
-            GNNA_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join[dev][sl], 0));
-        }
     }
     if (sparse > 0) {
         GNNA_REQUIRE(send_idx || max_chunks == 0, "halo_push_ce: null send_idx");

@@ -61,10 +61,20 @@ static int get_handle(cublasHandle_t *h)
 }
 
 // C[m,n] = op(A) * op(B), all row-major.  Row-major C = A*B is column-major C^T = B^T * A^T.
+// row_scale / scaled: the caller would like C[i,:] *= row_scale[i]; *scaled says whether this call did it (only the
+// tensor-core path has that epilogue, otherwise the caller runs its pre-scale pass).
 static int sgemm_rm(cudaStream_t st, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
-                    const float *A, const float *B, float *C)
+                    const float *A, const float *B, float *C, const float *row_scale = nullptr, bool *scaled = nullptr)
 {
+    if (scaled) *scaled = false;
     if (m == 0 || n == 0) return GNNA_OK;
+    if (tc_gemm_enabled() && k > 0) {      // the two tall-skinny contractions of a layer: tcgen05, 3xTF32 (gemm_tf32x3.cu)
+        const int rc = gemm_tf32x3(st, ta, tb, m, n, k, A, B, C, (!ta && scaled) ? row_scale : nullptr);
+        if (rc != GNNA_ERR_UNSUPPORTED) {
+            if (rc == GNNA_OK && scaled && row_scale && !ta) *scaled = true;
+            return rc;
+        }
+    }
     cublasHandle_t h;
     int rc = get_handle(&h);
     if (rc != GNNA_OK) return rc;
@@ -225,10 +235,12 @@ extern "C" int gnna_forward_f32(const float *X, const float *W, float *T_ws, flo
     cudaStream_t st = (cudaStream_t)stream;
     GNNA_REQUIRE(X && W && T_ws && out, "gnna_forward_f32: null pointer");
     GNNA_REQUIRE(degrees, "gnna_forward_f32: null degrees");
-    GNNA_TRY(sgemm_rm(st, false, false, num_nodes, dout, din, X, W, T_ws));               // kernel.cu:280
+    const bool prescale = !gcn_exact_mode();
+    bool scaled = false;
+    GNNA_TRY(sgemm_rm(st, false, false, num_nodes, dout, din, X, W, T_ws, prescale ? degrees : nullptr, &scaled));   // kernel.cu:280
     int mode = MODE_GCN;
-    if (!gcn_exact_mode()) {   // T is our own scratch: pre-scale it in place, no extra buffer
-        GNNA_TRY(prescale_rows(T_ws, T_ws, degrees, num_nodes, dout, st));
+    if (prescale) {            // T is our own scratch: rows scaled by n_j in the product's epilogue, else in place afterwards
+        if (!scaled) GNNA_TRY(prescale_rows(T_ws, T_ws, degrees, num_nodes, dout, st));
         mode = MODE_GCN_PRESCALED;
     }
     return aggregate(mode, 4, T_ws, out, row_ptr, col_idx, degrees, 1.f, part_ptr, part2node, num_nodes, dout,

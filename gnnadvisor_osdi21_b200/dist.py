@@ -287,8 +287,11 @@ class ShardedGraph:
         kmode = 3 if mode == 1 else mode
         p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
         st = ctypes.c_void_p(cur.cuda_stream)
-        if os.environ.get("GNNA_GATED", "1") == "1":
-            # ONE kernel: the CTAs of a peer's segment wait for that peer's flag inside the kernel (csrc/aggregate.cu)
+        # ONE kernel whose CTAs wait for a peer's flag inside the kernel (csrc/aggregate.cu) against one kernel per owner
+        # sub-shard with wait kernels in between: measured on the Reddit look-alike (profiles/r02_*sweep*, ab_gated) the fused
+        # kernel wins where the sub-kernels are short -- 8 GPUs: 0.304 vs 0.324 ms -- and loses 2-3 % at 2 and 4 GPUs (every CTA
+        # of a peer segment pays the flag round trip).  GNNA_GATED=0/1 forces either.
+        if os.environ.get("GNNA_GATED", "1" if self.world >= 8 else "0") == "1":
             _lib.check(lib.gnna_aggregate_gated_f32(kmode, p(x_ext), self.n_ext, p(out), self.n_local, p(self.row_ptr),
                                                     p(self.gated_col), p(self.degrees_ext) if kmode == 3 else ctypes.c_void_p(0),
                                                     float(eps), p(self.gated_pp), p(self.gated_pn), d, self.gated_pn.numel(),

@@ -335,6 +335,12 @@ GNNA_API int gnna_set_gcn_exact(int on);
  * semantics and rounding as the general path.  Returns the previous limit.                                    */
 GNNA_API int64_t gnna_set_small_parts(int64_t limit);
 
+/* 1 (default; GNNA_TC_GEMM=0 in the environment switches it off) = the two tall-skinny contractions of a layer -- X*W with
+ * >= 8192 rows and K >= 64, X^T*G reduced over >= 8192 rows, n <= 128 -- run on the tensor cores (csrc/gemm_tf32x3.cu: tcgen05
+ * kind::tf32 with the 3xTF32 split, fp32-grade accuracy) instead of cuBLAS' SIMT SGEMM; every other product stays a cuBLAS
+ * SGEMM as torch::mm is in the reference.  Returns the previous setting.                                        */
+GNNA_API int gnna_set_tc_gemm(int on);
+
 /* 1 = use the persistent kernel that streams the group table and the column indices through TMA bulk copies
  * (cp.async.bulk) into a shared-memory ring (csrc/aggregate_staged.cu) where it applies (fp32, dim % 4 == 0,
  * 8 <= dim <= 128, part_size <= 64); 0 (default) = the occupancy-driven kernel (csrc/aggregate.cu).  Also

@@ -797,6 +797,69 @@ def test_pair_stream_kernel_equals_the_torch_definition(kind, n):
     assert torch.equal(rp_g.cpu(), rp_c) and torch.equal(ci_g.cpu(), ci_c)
 
 
+def _sgemm(A, B, ta=False):
+    import ctypes
+    from gnnadvisor_osdi21_b200 import _lib
+    m = A.shape[1] if ta else A.shape[0]
+    k = A.shape[0] if ta else A.shape[1]
+    n = B.shape[1]
+    C = torch.full((m, n), float("nan"), device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+    _lib.check(_lib.load().gnna_sgemm_f32(int(ta), 0, m, n, k, p(A), p(B), p(C), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "sgemm")
+    return C
+
+
+@pytest.mark.parametrize("m,k,n", [(10000, 602, 64), (9000, 100, 47), (8200, 64, 16), (8200, 65, 8), (8229, 128, 128),
+                                   (58241, 602, 41), (8192, 1433, 16)])
+def test_tensor_core_gemm_nn_is_fp32_grade(m, k, n):
+    """X*W on the tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32, 3xTF32 split) against a float64 product:
+    the error is bounded by 4e-6 of the absolute terms -- SGEMM-grade, 25x inside the 1e-4 parity bar -- for every copy
+    width (K % 4 == 0, even, odd), ragged row tiles, N not a multiple of 16, and it agrees with the cuBLAS path."""
+    from gnnadvisor_osdi21_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(m + k + n)
+    A = torch.randn(m, k, device=DEV, generator=g)
+    B = torch.randn(k, n, device=DEV, generator=g)
+    _lib.launch_count(reset=True)
+    C = _sgemm(A, B)
+    assert _lib.launch_count() == 1                      # our kernel, not a cuBLAS call
+    ref = A.double() @ B.double()
+    terms = A.abs().double() @ B.abs().double()
+    assert bool(torch.isfinite(C).all())
+    assert float(((C.double() - ref).abs() / terms).max()) <= 4e-6
+    prev = _lib.set_tc_gemm(False)
+    try:
+        Cb = _sgemm(A, B)
+    finally:
+        _lib.set_tc_gemm(prev)
+    assert float(((Cb.double() - ref).abs() / terms).max()) <= 4e-6
+    assert float(((C - Cb).abs().double() / terms).max()) <= 4e-6
+
+
+@pytest.mark.parametrize("rows,m,n", [(12000, 602, 64), (9000, 100, 47), (8200, 64, 41), (60000, 33, 7), (8192, 128, 128)])
+def test_tensor_core_gemm_tn_is_fp32_grade(rows, m, n):
+    """X^T*G (reduced over the node dimension, split over the SMs, merged with reductions) against a float64 product."""
+    from gnnadvisor_osdi21_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(rows + m + n)
+    A = torch.randn(rows, m, device=DEV, generator=g)
+    B = torch.randn(rows, n, device=DEV, generator=g)
+    _lib.launch_count(reset=True)
+    C = _sgemm(A, B, ta=True)
+    assert _lib.launch_count() == 1
+    ref = A.double().t() @ B.double()
+    terms = A.abs().double().t() @ B.abs().double()
+    assert bool(torch.isfinite(C).all())
+    assert float(((C.double() - ref).abs() / terms).max()) <= 4e-6
+
+
+def test_small_or_odd_products_stay_on_cublas():
+    from gnnadvisor_osdi21_b200 import _lib
+    A, B = torch.randn(500, 48, device=DEV), torch.randn(48, 16, device=DEV)
+    _lib.launch_count(reset=True)
+    C = _sgemm(A, B)
+    assert _lib.launch_count() == 0                      # cuBLAS launches are not counted as ours
+    assert torch.allclose(C, A @ B, rtol=1e-4, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------ single-launch path (small graphs)
 def _launches(fn):
     from gnnadvisor_osdi21_b200 import _lib
