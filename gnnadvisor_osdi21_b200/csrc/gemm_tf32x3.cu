@@ -16,8 +16,10 @@
 //     (8-row x 16-byte core matrices): a warp fills whole core matrices, so shared-memory writes are conflict-free and every
 //     32-byte sector fetched is used.  TMA cannot serve this path: X's row pitch (602 * 4 = 2408 bytes) is not a multiple of
 //     16 bytes, which cuTensorMapEncodeTiled requires.  The TN product transposes while it loads (4-byte copies);
-//   * 4 raw stages (2 k-blocks in flight while one is split and one multiplied), split tiles double buffered; the elected
-//     thread issues 12 MMAs per k-block and `tcgen05.commit`s to the mbarrier that frees the buffers;
+//   * R raw stages (7 for N <= 64, 5 up to N = 128: what 227 KB of shared memory hold), R - 2 k-blocks in flight while one is
+//     split and one multiplied -- 80 KB of loads per SM in flight, what it takes to pull HBM bandwidth through one CTA per
+//     SM (with 2 in flight the first version ran at cuBLAS-SIMT speed) -- split tiles double buffered; the elected thread
+//     issues 12 MMAs per k-block and `tcgen05.commit`s to the mbarrier that frees the buffers;
 //   * persistent CTAs (one per SM) over row tiles (NN) or over a split of the node range (TN, merged with red.global.add);
 //     the loads of the next tile are already in flight while TMEM is drained by tcgen05.ld.
 #include <string.h>
@@ -30,7 +32,6 @@ namespace {
 
 constexpr int GT_M = 128;          // rows of the accumulator tile (UMMA M)
 constexpr int GT_BK = 32;          // fp32 elements of K per k-block: 128 bytes = 8 core matrices per row
-constexpr int GT_RAW = 4;          // raw stages
 constexpr int GT_THREADS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,10 +169,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem, uint64_t adesc, uint64_t
 
 // TRANS = false: NN (A rows K-major in memory, B transposed while loading).  TRANS = true: TN (both operands transposed
 // while loading, reduced dimension split over gridDim.y CTAs, result merged with reductions).  CP: copy size for A (NN only).
-template <bool TRANS, int CP>
+template <bool TRANS, int CP, int GT_RAW>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tf32x3_kernel(const GemmArgs g)
 {
+    constexpr int DIST = GT_RAW - 2;               // k-blocks in flight
     extern __shared__ __align__(1024) unsigned char smem[];
     const int npad = g.npad;
     const int a_bytes = GT_M * GT_BK * 4, b_bytes = npad * GT_BK * 4;
@@ -231,18 +233,18 @@ gemm_tf32x3_kernel(const GemmArgs g)
         }
     };
 
-    // prologue: two k-blocks in flight
-    for (int q = 0; q < 2; q++) {
+    // prologue: DIST k-blocks in flight
+    for (int q = 0; q < DIST; q++) {
         if (q < total) issue_loads(q);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
     for (long long q = 0; q < total; q++) {
         const int st = (int)(q % GT_RAW), lb = (int)(q & 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");       // this thread's copies of k-block q have landed
+        asm volatile("cp.async.wait_group %0;" ::"n"(DIST - 1) : "memory");   // this thread's copies of k-block q have landed
         __syncthreads();                                           // ... and everybody else's
-        if (q >= 2) mbar_wait(&bars[lb], (uint32_t)(((q - 2) >> 1) & 1));   // MMAs of k-block q-2 done: lo[lb], raw[(q+2)%4] free
-        if (q + 2 < total) issue_loads(q + 2);
+        if (q >= 2) mbar_wait(&bars[lb], (uint32_t)(((q - 2) >> 1) & 1));   // MMAs of k-block q-2 done: lo[lb] and raw stage
+        if (q + DIST < total) issue_loads(q + DIST);                        // (q + DIST) % GT_RAW == (q - 2) % GT_RAW are free
         asm volatile("cp.async.commit_group;" ::: "memory");
         split_tile(reinterpret_cast<float *>(raw_a + st * a_bytes), reinterpret_cast<float *>(lo_a + lb * a_bytes), a_bytes);
         split_tile(reinterpret_cast<float *>(raw_b + st * b_bytes), reinterpret_cast<float *>(lo_b + lb * b_bytes), b_bytes);
@@ -312,7 +314,23 @@ gemm_tf32x3_kernel(const GemmArgs g)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
-static int gemm_smem_bytes(int npad) { return (GT_RAW + 2) * (GT_M * GT_BK * 4 + npad * GT_BK * 4) + 64; }
+static int gemm_smem_bytes(int npad, int raw) { return (raw + 2) * (GT_M * GT_BK * 4 + npad * GT_BK * 4) + 64; }
+
+template <bool TRANS, int CP, int RAW>
+static int launch_gemm(const GemmArgs &g, dim3 grid, cudaStream_t st)
+{
+    const int smem = gemm_smem_bytes(g.npad, RAW);
+    GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<TRANS, CP, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm_tf32x3_kernel<TRANS, CP, RAW><<<grid, GT_THREADS, smem, st>>>(g);
+    GNNA_CUDA_CHECK(cudaGetLastError());
+    return GNNA_OK;
+}
+
+template <bool TRANS, int CP>
+static int launch_gemm_raw(const GemmArgs &g, dim3 grid, cudaStream_t st)
+{
+    return g.npad <= 64 ? launch_gemm<TRANS, CP, 7>(g, grid, st) : launch_gemm<TRANS, CP, 5>(g, grid, st);
+}
 
 static int g_tc_gemm = -1;     // -1: environment (GNNA_TC_GEMM, default on), 0 off, 1 on
 bool tc_gemm_enabled()
@@ -340,27 +358,22 @@ int gemm_tf32x3(cudaStream_t st, bool ta, bool tb, int64_t m, int64_t n, int64_t
     int dev = 0, sms = 148;
     GNNA_CUDA_CHECK(cudaGetDevice(&dev));
     GNNA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int smem = gemm_smem_bytes(g.npad);
     if (!ta) {
-        // NN: worth it when A is tall (many row tiles) and K is a real contraction
-        if (m < 8192 || k < 64 || k > 0x7fffffff) return GNNA_ERR_UNSUPPORTED;
+        // NN: worth it when A is tall (many row tiles) and K is a real contraction (for K < 256 the per-tile epilogue
+        // dominates and cuBLAS' SIMT kernel is as fast)
+        if (m < 8192 || k < 256 || k > 0x7fffffff) return GNNA_ERR_UNSUPPORTED;
         g.M = m; g.K = (int)k;
         g.work = (m + GT_M - 1) / GT_M;
-        const int grid = (int)(g.work < sms ? g.work : sms);
+        const dim3 grid((unsigned)(g.work < sms ? g.work : sms));
         const bool a16 = (k % 4 == 0) && (((uintptr_t)A & 15) == 0), a8 = (k % 2 == 0) && (((uintptr_t)A & 7) == 0);
-        if (a16) {
-            GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            gemm_tf32x3_kernel<false, 16><<<grid, GT_THREADS, smem, st>>>(g);
-        } else if (a8) {
-            GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            gemm_tf32x3_kernel<false, 8><<<grid, GT_THREADS, smem, st>>>(g);
-        } else {
-            GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            gemm_tf32x3_kernel<false, 4><<<grid, GT_THREADS, smem, st>>>(g);
-        }
+        int rc;
+        if (a16) rc = launch_gemm_raw<false, 16>(g, grid, st);
+        else if (a8) rc = launch_gemm_raw<false, 8>(g, grid, st);
+        else rc = launch_gemm_raw<false, 4>(g, grid, st);
+        if (rc != GNNA_OK) return rc;
     } else {
         // TN: C[m, n] = A[k, m]^T B[k, n], reduced over k (the node dimension): split over the SMs, merged with reductions
-        if (row_scale || k < 8192 || m < 32 || m > 0x7fffffff) return GNNA_ERR_UNSUPPORTED;
+        if (row_scale || k < 8192 || m < 256 || m > 0x7fffffff) return GNNA_ERR_UNSUPPORTED;
         g.M = k; g.K = (int)m;
         const int m_tiles = (int)((m + GT_M - 1) / GT_M);
         const long long total_kb = (k + GT_BK - 1) / GT_BK;
@@ -370,8 +383,8 @@ int gemm_tf32x3(cudaStream_t st, bool ta, bool tb, int64_t m, int64_t n, int64_t
         g.work = (total_kb + splits - 1) / splits;
         g.splits = splits;
         GNNA_CUDA_CHECK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)m * (size_t)n, st));
-        GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        gemm_tf32x3_kernel<true, 4><<<dim3(m_tiles, splits), GT_THREADS, smem, st>>>(g);
+        const int rc = launch_gemm_raw<true, 4>(g, dim3(m_tiles, splits), st);
+        if (rc != GNNA_OK) return rc;
     }
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);

@@ -809,7 +809,7 @@ def _sgemm(A, B, ta=False):
     return C
 
 
-@pytest.mark.parametrize("m,k,n", [(10000, 602, 64), (9000, 100, 47), (8200, 64, 16), (8200, 65, 8), (8229, 128, 128),
+@pytest.mark.parametrize("m,k,n", [(10000, 602, 64), (9000, 300, 47), (8200, 257, 16), (8200, 1001, 8), (8229, 256, 128),
                                    (58241, 602, 41), (8192, 1433, 16)])
 def test_tensor_core_gemm_nn_is_fp32_grade(m, k, n):
     """X*W on the tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32, 3xTF32 split) against a float64 product:
@@ -835,7 +835,7 @@ def test_tensor_core_gemm_nn_is_fp32_grade(m, k, n):
     assert float(((C - Cb).abs().double() / terms).max()) <= 4e-6
 
 
-@pytest.mark.parametrize("rows,m,n", [(12000, 602, 64), (9000, 100, 47), (8200, 64, 41), (60000, 33, 7), (8192, 128, 128)])
+@pytest.mark.parametrize("rows,m,n", [(12000, 602, 64), (9000, 300, 47), (8200, 256, 41), (60000, 257, 7), (8192, 384, 128)])
 def test_tensor_core_gemm_tn_is_fp32_grade(rows, m, n):
     """X^T*G (reduced over the node dimension, split over the SMs, merged with reductions) against a float64 product."""
     from gnnadvisor_osdi21_b200 import _lib

@@ -24,6 +24,12 @@ W = torch.eye(D, device=dev)
 a = (rp, ci, deg, pp, pn, 32, 32, 4)
 ops.forward(X, W, *a)                                             # SGEMM + repack_rows (pre-scale) + aggregate_kernel fp32
 ops.forward_gin(X, W, rp, ci, 0.5, pp, pn, 32, 32, 4)             # aggregate_kernel fp32 (GIN flags)
+if wl == "reddit":                                                # the layer-1 products: gemm_tf32x3_kernel NN (X*W) and TN (X^T*G)
+    X602 = torch.randn(N, 602, device=dev)
+    W602 = torch.randn(602, D, device=dev) / 8
+    ops.forward(X602, W602, *a)
+    ops.backward(X, X602, W602, *a, need_d_input=False)
+    del X602
 Xb = ops.scale_rows_bf16(X, deg)                                  # scale_rows_bf16_kernel
 ops.aggregate_bf16(3, Xb, rp, ci, deg, 1.0, pp, pn, 32, 32, 4)    # aggregate_runs (bf16) by the library's rule
 prev = _lib.set_runs(0)
