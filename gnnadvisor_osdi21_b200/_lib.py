@@ -130,10 +130,11 @@ def set_gcn_exact(on):
     return bool(load().gnna_set_gcn_exact(1 if on else 0))
 
 
-def set_tc_gemm(on):
-    """True (default): the tall-skinny products of a layer run on the tensor cores (tcgen05 kind::tf32, 3xTF32 split);
-    False: every product is a cuBLAS SGEMM.  Returns the previous setting."""
-    return bool(load().gnna_set_tc_gemm(1 if on else 0))
+def set_tc_gemm(mode):
+    """0 (default): every dense product is a cuBLAS SGEMM.  1 / 2: the tall-skinny products of a layer (X*W, X^T*G) run on the
+    tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32, 3xTF32 split) -- 1 the lockstep kernel, 2 the warp-specialised
+    one.  Also GNNA_TC_GEMM in the environment.  Returns the previous mode."""
+    return int(load().gnna_set_tc_gemm(int(mode)))
 
 
 def set_small_parts(limit):

@@ -68,6 +68,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// bounded wait (a protocol bug traps instead of hanging the GPU): ~2^28 polls are seconds
+__device__ __forceinline__ void mbar_wait_b(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > (1u << 28)) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// the barrier receives one arrival from this thread when all cp.async it issued so far have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // cp.async of CP bytes with zero fill of the bytes beyond `valid` (0 <= valid <= CP); src must be a valid address even
 // when valid == 0 (nothing is read then)
 template <int CP>
@@ -99,12 +123,12 @@ struct GemmArgs {
 // shared memory.  CP = copy size the alignment of A allows (16, 8 or 4 bytes).
 template <int CP>
 __device__ __forceinline__ void load_rows_kmajor(uint32_t tile, const float *base, long long row0, long long rows_total, int ld, int k0,
-                                                 int k_total, int tile_rows)
+                                                 int k_total, int tile_rows, int t = threadIdx.x, int nthreads = GT_THREADS)
 {
     constexpr int PER = 16 / CP;                            // copies per 16-byte chunk
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int lane = t & 31, warp = t >> 5;
     const int chunks = tile_rows * 8;                       // 16-byte chunks in the tile
-    for (int c0 = warp * 32; c0 < chunks; c0 += (GT_THREADS / 32) * 32) {
+    for (int c0 = warp * 32; c0 < chunks; c0 += nthreads) {
         // 32 consecutive chunks in SHARED memory order = 4 core matrices: chunk index -> (group of 8 rows, k/4, row % 8)
         const int c = c0 + lane;
         const int rg = c >> 6, kc = (c >> 3) & 7, r8 = c & 7;
@@ -126,11 +150,11 @@ __device__ __forceinline__ void load_rows_kmajor(uint32_t tile, const float *bas
 // lane -> (k % 4 = lane % 4, row % 8 = lane / 4): one core matrix (128 contiguous bytes of shared memory) per warp request,
 // 4 global rows x 32 contiguous bytes on the global side.
 __device__ __forceinline__ void load_cols_kmajor(uint32_t tile, const float *base, int col0, int cols_total, int ld, long long k0,
-                                                 long long k_total, int tile_rows)
+                                                 long long k_total, int tile_rows, int t = threadIdx.x, int nthreads = GT_THREADS)
 {
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int lane = t & 31, warp = t >> 5;
     const int cms = tile_rows;                              // core matrices in the tile: (tile_rows / 8) * 8
-    for (int cm = warp; cm < cms; cm += GT_THREADS / 32) {
+    for (int cm = warp; cm < cms; cm += nthreads / 32) {
         const int rg = cm >> 3, kc = cm & 7;
         const int r = rg * 8 + (lane >> 2), k = kc * 4 + (lane & 3);
         const long long gk = k0 + k;
@@ -142,10 +166,10 @@ __device__ __forceinline__ void load_cols_kmajor(uint32_t tile, const float *bas
 }
 
 // hi/lo split of a tile in place: raw -> hi (same buffer), lo (second buffer).  Element-wise, layout-agnostic, 128-bit.
-__device__ __forceinline__ void split_tile(float *raw, float *lo, int bytes)
+__device__ __forceinline__ void split_tile(float *raw, float *lo, int bytes, int t = threadIdx.x, int nthreads = GT_THREADS)
 {
     const int n4 = bytes >> 4;
-    for (int i = threadIdx.x; i < n4; i += GT_THREADS) {
+    for (int i = t; i < n4; i += nthreads) {
         float4 v = reinterpret_cast<float4 *>(raw)[i];
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -314,14 +338,178 @@ gemm_tf32x3_kernel(const GemmArgs g)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
-static int gemm_smem_bytes(int npad, int raw) { return (raw + 2) * (GT_M * GT_BK * 4 + npad * GT_BK * 4) + 64; }
+
+// ---- warp-specialised variant ------------------------------------------------------------------------------------
+// The lockstep kernel above spends ~700 cycles of SOFTWARE per k-block (every warp issues copies, splits, then waits while
+// one thread issues the MMAs, with two CTA-wide barriers in between) -- as long as the k-block's HBM time, so it ran at
+// cuBLAS-SIMT speed (measured: GCN epoch 8.27 vs 7.78 ms).  Here the three jobs run side by side, coupled by mbarriers only:
+//   warps 0-3  PRODUCERS   cp.async the raw A/B tiles of k-block q into stage q % R as soon as the MMAs that last read the
+//                          stage have retired (empty[stage], arrived by tcgen05.commit); completion -> full[stage]
+//                          (cp.async.mbarrier.arrive.noinc, one arrival per producer thread);
+//   warps 4-7  CONVERTERS  wait full[stage] and the lo buffer (done[q & 1] of k-block q-2), split raw -> hi (in place) + lo,
+//                          fence to the async proxy, arrive ready[q & 1]; at the end of a tile they wait for its last MMAs and
+//                          drain TMEM (they are the four warps whose TMEM lane quarter is warp % 4);
+//   warp 8     MMA         one thread: wait ready[q & 1], issue the 12 MMAs, commit to empty[stage] and done[q & 1].
+// The next tile's first MMA is ordered after the drain of TMEM because its ready[] arrival comes from the same converter
+// threads, after their epilogue.
+constexpr int WS_PROD = 128, WS_CONV = 128, WS_THREADS = WS_PROD + WS_CONV + 32;
+
+template <bool TRANS, int CP, int GT_RAW>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+gemm_tf32x3_ws_kernel(const GemmArgs g)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int npad = g.npad;
+    const int a_bytes = GT_M * GT_BK * 4, b_bytes = npad * GT_BK * 4;
+    unsigned char *raw_a = smem;
+    unsigned char *raw_b = raw_a + GT_RAW * a_bytes;
+    unsigned char *lo_a = raw_b + GT_RAW * b_bytes;
+    unsigned char *lo_b = lo_a + 2 * a_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(lo_b + 2 * b_bytes);   // [GT_RAW] raw tiles landed         (128 cp.async arrivals)
+    uint64_t *empty = full + GT_RAW;                                      // [GT_RAW] raw stage may be refilled (1 commit)
+    uint64_t *ready = empty + GT_RAW;                                     // [2] hi/lo tiles are in place      (128 converter arrivals)
+    uint64_t *done = ready + 2;                                           // [2] MMAs of this lo buffer retired (1 commit)
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(done + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tmem_cols = 32;
+    while (tmem_cols < npad) tmem_cols *= 2;
+    if (tid == 0) {
+        for (int i = 0; i < GT_RAW; i++) { mbar_init(&full[i], WS_PROD); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&ready[i], WS_CONV); mbar_init(&done[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+
+    long long n_tiles, kb_per_tile;
+    if (!TRANS) {
+        n_tiles = ((long long)blockIdx.x < g.work) ? (g.work - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        kb_per_tile = (g.K + GT_BK - 1) / GT_BK;
+    } else {
+        const long long total_kb = (g.M + GT_BK - 1) / GT_BK;
+        const long long first = (long long)blockIdx.y * g.work;
+        kb_per_tile = first < total_kb ? min(g.work, total_kb - first) : 0;
+        n_tiles = kb_per_tile > 0 ? 1 : 0;
+    }
+    const long long total = n_tiles * kb_per_tile;
+
+    if (warp < 4) {
+        // ===== PRODUCERS
+        for (long long q = 0; q < total; q++) {
+            const int st = (int)(q % GT_RAW);
+            const uint32_t fill = (uint32_t)(q / GT_RAW);
+            mbar_wait_b(&empty[st], (fill & 1) ^ 1);                // passes at once on a fresh barrier
+            const uint32_t ta = smem_u32(raw_a + st * a_bytes), tb = smem_u32(raw_b + st * b_bytes);
+            if (!TRANS) {
+                const long long tile = blockIdx.x + (q / kb_per_tile) * gridDim.x;
+                const int k0 = (int)(q % kb_per_tile) * GT_BK;
+                load_rows_kmajor<CP>(ta, g.A, tile * GT_M, g.M, g.K, k0, g.K, GT_M, tid, WS_PROD);
+                load_cols_kmajor(tb, g.B, 0, g.N, g.N, k0, g.K, npad, tid, WS_PROD);
+            } else {
+                const long long k0 = ((long long)blockIdx.y * g.work + q) * GT_BK;
+                load_cols_kmajor(ta, g.A, blockIdx.x * GT_M, g.K, g.K, k0, g.M, GT_M, tid, WS_PROD);
+                load_cols_kmajor(tb, g.B, 0, g.N, g.N, k0, g.M, npad, tid, WS_PROD);
+            }
+            cp_async_arrive(&full[st]);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp < 8) {
+        // ===== CONVERTERS (+ epilogue)
+        const int ct = tid - WS_PROD;
+        for (long long q = 0; q < total; q++) {
+            const int st = (int)(q % GT_RAW), lb = (int)(q & 1);
+            const uint32_t fill = (uint32_t)(q / GT_RAW), use = (uint32_t)(q >> 1);
+            mbar_wait_b(&full[st], fill & 1);
+            mbar_wait_b(&done[lb], (use & 1) ^ 1);                  // MMAs of k-block q-2 retired: lo[lb] is free
+            split_tile(reinterpret_cast<float *>(raw_a + st * a_bytes), reinterpret_cast<float *>(lo_a + lb * a_bytes), a_bytes, ct, WS_CONV);
+            split_tile(reinterpret_cast<float *>(raw_b + st * b_bytes), reinterpret_cast<float *>(lo_b + lb * b_bytes), b_bytes, ct, WS_CONV);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&ready[lb]);
+            const long long kb_in_tile = q % kb_per_tile;
+            if (kb_in_tile == kb_per_tile - 1) {
+                mbar_wait_b(&done[lb], use & 1);                    // the tile's last MMAs retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int qd = warp & 3;
+                const int r_in_tile = qd * 32 + lane;
+                long long row;
+                if (!TRANS) row = (blockIdx.x + (q / kb_per_tile) * gridDim.x) * GT_M + r_in_tile;
+                else row = (long long)blockIdx.x * GT_M + r_in_tile;
+                const long long rows_total = TRANS ? g.K : g.M;
+                float rs = 1.f;
+                if (!TRANS && g.row_scale && row < rows_total) rs = __ldg(g.row_scale + row);
+                for (int c = 0; c < npad; c += 16) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row < rows_total) {
+                        float *o = g.C + row * g.N + c;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            if (c + j < g.N) {
+                                const float v = __uint_as_float(r[j]);
+                                if (!TRANS) o[j] = g.row_scale ? __fmul_rn(rs, v) : v;
+                                else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + j), "f"(v) : "memory");
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads ordered before the next ready[] arrival
+            }
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer (one thread)
+        const uint32_t idesc = idesc_tf32(GT_M, npad);
+        for (long long q = 0; q < total; q++) {
+            const int st = (int)(q % GT_RAW), lb = (int)(q & 1);
+            const uint32_t use = (uint32_t)(q >> 1);
+            mbar_wait_b(&ready[lb], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long kb_in_tile = q % kb_per_tile;
+            const uint32_t a_hi = smem_u32(raw_a + st * a_bytes), a_lo = smem_u32(lo_a + lb * a_bytes);
+            const uint32_t b_hi = smem_u32(raw_b + st * b_bytes), b_lo = smem_u32(lo_b + lb * b_bytes);
+#pragma unroll
+            for (int ks = 0; ks < GT_BK / 8; ks++) {
+                const uint32_t o = ks * 256;
+                mma_tf32(tmem_base, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kb_in_tile > 0 || ks > 0) ? 1u : 0u);
+                mma_tf32(tmem_base, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1u);
+                mma_tf32(tmem_base, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1u);
+            }
+            umma_commit(&empty[st]);
+            umma_commit(&done[lb]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+}
+
+static int gemm_smem_bytes(int npad, int raw) { return (raw + 2) * (GT_M * GT_BK * 4 + npad * GT_BK * 4) + 8 * (2 * raw + 4) + 64; }
+
+static int g_tc_gemm = -1;     // -1: environment (GNNA_TC_GEMM), 0 cuBLAS only, 1 lockstep kernel, 2 warp-specialised kernel
 
 template <bool TRANS, int CP, int RAW>
 static int launch_gemm(const GemmArgs &g, dim3 grid, cudaStream_t st)
 {
     const int smem = gemm_smem_bytes(g.npad, RAW);
-    GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<TRANS, CP, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm_tf32x3_kernel<TRANS, CP, RAW><<<grid, GT_THREADS, smem, st>>>(g);
+    if (g_tc_gemm == 2) {
+        GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_ws_kernel<TRANS, CP, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        gemm_tf32x3_ws_kernel<TRANS, CP, RAW><<<grid, WS_THREADS, smem, st>>>(g);
+    } else {
+        GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<TRANS, CP, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        gemm_tf32x3_kernel<TRANS, CP, RAW><<<grid, GT_THREADS, smem, st>>>(g);
+    }
     GNNA_CUDA_CHECK(cudaGetLastError());
     return GNNA_OK;
 }
@@ -332,14 +520,13 @@ static int launch_gemm_raw(const GemmArgs &g, dim3 grid, cudaStream_t st)
     return g.npad <= 64 ? launch_gemm<TRANS, CP, 7>(g, grid, st) : launch_gemm<TRANS, CP, 5>(g, grid, st);
 }
 
-static int g_tc_gemm = -1;     // -1: environment (GNNA_TC_GEMM, default on), 0 off, 1 on
 bool tc_gemm_enabled()
 {
     if (g_tc_gemm < 0) {
         const char *e = getenv("GNNA_TC_GEMM");
-        g_tc_gemm = (e && e[0] == '0') ? 0 : 1;
+        g_tc_gemm = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
     }
-    return g_tc_gemm == 1;
+    return g_tc_gemm >= 1;
 }
 
 // C[m, n] = op(A) * B on the tensor cores where the shape is one of the two tall-skinny contractions of a layer; returns
@@ -393,9 +580,10 @@ int gemm_tf32x3(cudaStream_t st, bool ta, bool tb, int64_t m, int64_t n, int64_t
 
 }  // namespace gnna
 
-extern "C" int gnna_set_tc_gemm(int on)
+extern "C" int gnna_set_tc_gemm(int mode)
 {
-    const int prev = gnna::tc_gemm_enabled() ? 1 : 0;
-    gnna::g_tc_gemm = on ? 1 : 0;
+    gnna::tc_gemm_enabled();
+    const int prev = gnna::g_tc_gemm;
+    gnna::g_tc_gemm = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
     return prev;
 }

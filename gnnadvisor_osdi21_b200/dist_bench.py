@@ -59,7 +59,7 @@ def run(args, bench):
     t_gen = time.perf_counter() - t_gen
     # features are a function of the GLOBAL row id (graph.stream_features): a rank makes its own rows, the checker any row
     own_ids = torch.arange(sg.v0, sg.v0 + sg.n_local, device=device)
-    X_local = torch.cat([graph.stream_features(own_ids[i:i + (1 << 22)], D) for i in range(0, max(sg.n_local, 1), 1 << 22)])
+    X_local = torch.cat([graph.stream_features(own_ids[i:i + (1 << 20)], D) for i in range(0, max(sg.n_local, 1), 1 << 20)])
     del own_ids
     torch.cuda.empty_cache()
     out = torch.empty(sg.n_local, D, device=device)

@@ -809,9 +809,18 @@ def _sgemm(A, B, ta=False):
     return C
 
 
+@pytest.fixture(params=[1, 2], ids=["lockstep", "warp-specialised"])
+def tc_gemm(request):
+    """The tensor-core products are opt-in (GNNA_TC_GEMM / gnna_set_tc_gemm): 1 = lockstep kernel, 2 = warp-specialised."""
+    from gnnadvisor_osdi21_b200 import _lib
+    prev = _lib.set_tc_gemm(request.param)
+    yield request.param
+    _lib.set_tc_gemm(prev)
+
+
 @pytest.mark.parametrize("m,k,n", [(10000, 602, 64), (9000, 300, 47), (8200, 257, 16), (8200, 1001, 8), (8229, 256, 128),
                                    (58241, 602, 41), (8192, 1433, 16)])
-def test_tensor_core_gemm_nn_is_fp32_grade(m, k, n):
+def test_tensor_core_gemm_nn_is_fp32_grade(m, k, n, tc_gemm):
     """X*W on the tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32, 3xTF32 split) against a float64 product:
     the error is bounded by 4e-6 of the absolute terms -- SGEMM-grade, 25x inside the 1e-4 parity bar -- for every copy
     width (K % 4 == 0, even, odd), ragged row tiles, N not a multiple of 16, and it agrees with the cuBLAS path."""
@@ -826,7 +835,7 @@ def test_tensor_core_gemm_nn_is_fp32_grade(m, k, n):
     terms = A.abs().double() @ B.abs().double()
     assert bool(torch.isfinite(C).all())
     assert float(((C.double() - ref).abs() / terms).max()) <= 4e-6
-    prev = _lib.set_tc_gemm(False)
+    prev = _lib.set_tc_gemm(0)
     try:
         Cb = _sgemm(A, B)
     finally:
@@ -836,7 +845,7 @@ def test_tensor_core_gemm_nn_is_fp32_grade(m, k, n):
 
 
 @pytest.mark.parametrize("rows,m,n", [(12000, 602, 64), (9000, 300, 47), (8200, 256, 41), (60000, 257, 7), (8192, 384, 128)])
-def test_tensor_core_gemm_tn_is_fp32_grade(rows, m, n):
+def test_tensor_core_gemm_tn_is_fp32_grade(rows, m, n, tc_gemm):
     """X^T*G (reduced over the node dimension, split over the SMs, merged with reductions) against a float64 product."""
     from gnnadvisor_osdi21_b200 import _lib
     g = torch.Generator(device=DEV).manual_seed(rows + m + n)
@@ -851,7 +860,7 @@ def test_tensor_core_gemm_tn_is_fp32_grade(rows, m, n):
     assert float(((C.double() - ref).abs() / terms).max()) <= 4e-6
 
 
-def test_small_or_odd_products_stay_on_cublas():
+def test_small_or_odd_products_stay_on_cublas(tc_gemm):
     from gnnadvisor_osdi21_b200 import _lib
     A, B = torch.randn(500, 48, device=DEV), torch.randn(48, 16, device=DEV)
     _lib.launch_count(reset=True)
