@@ -131,9 +131,10 @@ def set_gcn_exact(on):
 
 
 def set_tc_gemm(mode):
-    """0 (default): every dense product is a cuBLAS SGEMM.  1 / 2: the tall-skinny products of a layer (X*W, X^T*G) run on the
-    tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32, 3xTF32 split) -- 1 the lockstep kernel, 2 the warp-specialised
-    one.  Also GNNA_TC_GEMM in the environment.  Returns the previous mode."""
+    """Which tall-skinny products of a layer (X*W, X^T*G) run on the tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32,
+    3xTF32 split): 0 none (cuBLAS SGEMM everywhere), 1 both on the lockstep kernel, 2 both on the warp-specialised kernel,
+    3 (default) X^T*G on the warp-specialised kernel and X*W on cuBLAS -- the measured winners.  Also GNNA_TC_GEMM in the
+    environment.  Returns the previous mode."""
     return int(load().gnna_set_tc_gemm(int(mode)))
 
 

@@ -125,24 +125,22 @@ template <int CP>
 __device__ __forceinline__ void load_rows_kmajor(uint32_t tile, const float *base, long long row0, long long rows_total, int ld, int k0,
                                                  int k_total, int tile_rows, int t = threadIdx.x, int nthreads = GT_THREADS)
 {
-    constexpr int PER = 16 / CP;                            // copies per 16-byte chunk
-    const int lane = t & 31, warp = t >> 5;
-    const int chunks = tile_rows * 8;                       // 16-byte chunks in the tile
-    for (int c0 = warp * 32; c0 < chunks; c0 += nthreads) {
-        // 32 consecutive chunks in SHARED memory order = 4 core matrices: chunk index -> (group of 8 rows, k/4, row % 8)
-        const int c = c0 + lane;
+    // The tile is filled in SHARED-memory order, CP bytes per lane: piece i lives at byte i * CP of the tile, i.e. in 16-byte
+    // chunk c = i * CP / 16 = (group of 8 rows, k / 4, row % 8).  A warp request therefore writes 32 * CP contiguous bytes
+    // (conflict-free) and reads, per row it touches, (16 / CP lanes) x CP = 16 contiguous bytes per chunk: with 8-byte copies
+    // the two halves of a chunk sit on neighbouring lanes, so every 32-byte sector a request touches is used completely
+    // (the first version put them in different instructions: half-used sectors, X*W at 1.0 TB/s).
+    constexpr int PER = 16 / CP;                            // pieces per 16-byte chunk
+    const int pieces = tile_rows * 8 * PER;
+    for (int i = t; i < pieces; i += nthreads) {
+        const int c = i / PER, h = i % PER;
         const int rg = c >> 6, kc = (c >> 3) & 7, r8 = c & 7;
-        const int r = rg * 8 + r8, k = kc * 4;
+        const int r = rg * 8 + r8, k = kc * 4 + h * (CP / 4);
         const long long grow = row0 + r;
-        const float *src = base + grow * ld + k0 + k;
-        const uint32_t dst = tile + (uint32_t)(rg * 1024 + kc * 128 + r8 * 16);
-#pragma unroll
-        for (int p = 0; p < PER; p++) {
-            const int kk = k0 + k + p * (CP / 4);
-            int valid = 0;
-            if (grow < rows_total && kk < k_total) valid = min(CP, (k_total - kk) * 4);
-            cp_async<CP>(dst + p * CP, valid ? (const void *)(src + p * (CP / 4)) : (const void *)base, valid);
-        }
+        const int kk = k0 + k;
+        int valid = 0;
+        if (grow < rows_total && kk < k_total) valid = min(CP, (k_total - kk) * 4);
+        cp_async<CP>(tile + (uint32_t)(c * 16 + h * CP), valid ? (const void *)(base + grow * ld + kk) : (const void *)base, valid);
     }
 }
 
@@ -497,13 +495,18 @@ gemm_tf32x3_ws_kernel(const GemmArgs g)
 
 static int gemm_smem_bytes(int npad, int raw) { return (raw + 2) * (GT_M * GT_BK * 4 + npad * GT_BK * 4) + 8 * (2 * raw + 4) + 64; }
 
-static int g_tc_gemm = -1;     // -1: environment (GNNA_TC_GEMM), 0 cuBLAS only, 1 lockstep kernel, 2 warp-specialised kernel
+// -1: not decided (environment GNNA_TC_GEMM, else 3); 0 cuBLAS only; 1 lockstep kernel for both products; 2 warp-specialised
+// kernel for both; 3 (default) = what the measurements say (tools/gemm_bench.py, profiles/r02_gemm_bench.txt, Reddit layer 1
+// on B200): X^T*G on the warp-specialised kernel (0.33 vs 0.42 ms for cuBLAS' SIMT SGEMM), X*W on cuBLAS (0.36 ms; the
+// kernel here needs 0.53 ms: with N = 64 the three MMAs of the split re-read a 16 KB A tile from shared memory per 8 KB of
+// B, and the split itself moves another 72 KB per k-block -- shared-memory bandwidth, not HBM, bounds it).
+static int g_tc_gemm = -1;
 
 template <bool TRANS, int CP, int RAW>
 static int launch_gemm(const GemmArgs &g, dim3 grid, cudaStream_t st)
 {
     const int smem = gemm_smem_bytes(g.npad, RAW);
-    if (g_tc_gemm == 2) {
+    if (g_tc_gemm >= 2) {
         GNNA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_ws_kernel<TRANS, CP, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         gemm_tf32x3_ws_kernel<TRANS, CP, RAW><<<grid, WS_THREADS, smem, st>>>(g);
     } else {
@@ -524,7 +527,7 @@ bool tc_gemm_enabled()
 {
     if (g_tc_gemm < 0) {
         const char *e = getenv("GNNA_TC_GEMM");
-        g_tc_gemm = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+        g_tc_gemm = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
     }
     return g_tc_gemm >= 1;
 }
@@ -547,8 +550,8 @@ int gemm_tf32x3(cudaStream_t st, bool ta, bool tb, int64_t m, int64_t n, int64_t
     GNNA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (!ta) {
         // NN: worth it when A is tall (many row tiles) and K is a real contraction (for K < 256 the per-tile epilogue
-        // dominates and cuBLAS' SIMT kernel is as fast)
-        if (m < 8192 || k < 256 || k > 0x7fffffff) return GNNA_ERR_UNSUPPORTED;
+        // dominates and cuBLAS' SIMT kernel is as fast); in the default mode cuBLAS keeps this product (see g_tc_gemm)
+        if (g_tc_gemm == 3 || m < 8192 || k < 256 || k > 0x7fffffff) return GNNA_ERR_UNSUPPORTED;
         g.M = m; g.K = (int)k;
         g.work = (m + GT_M - 1) / GT_M;
         const dim3 grid((unsigned)(g.work < sms ? g.work : sms));
@@ -584,6 +587,6 @@ extern "C" int gnna_set_tc_gemm(int mode)
 {
     gnna::tc_gemm_enabled();
     const int prev = gnna::g_tc_gemm;
-    gnna::g_tc_gemm = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+    gnna::g_tc_gemm = mode < 0 ? 0 : (mode > 3 ? 3 : mode);
     return prev;
 }

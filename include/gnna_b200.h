@@ -335,10 +335,11 @@ GNNA_API int gnna_set_gcn_exact(int on);
  * semantics and rounding as the general path.  Returns the previous limit.                                    */
 GNNA_API int64_t gnna_set_small_parts(int64_t limit);
 
-/* mode 1 or 2 (GNNA_TC_GEMM in the environment; default 0 = every product is a cuBLAS SGEMM as torch::mm is in the
- * reference): the two tall-skinny contractions of a layer -- X*W with >= 8192 rows and K >= 256, X^T*G reduced over >= 8192
- * rows with >= 256 columns, n <= 128 -- run on the tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32 with the 3xTF32
- * split, fp32-grade accuracy): 1 = the lockstep kernel, 2 = the warp-specialised one.  Returns the previous mode.   */
+/* Which dense products run on the tensor cores (csrc/gemm_tf32x3.cu: tcgen05 kind::tf32 with the 3xTF32 split, fp32-grade
+ * accuracy) instead of cuBLAS' SIMT SGEMM (what torch::mm is in the reference).  Candidates are the two tall-skinny
+ * contractions of a layer: X*W (>= 8192 rows, K >= 256) and X^T*G (reduced over >= 8192 rows, >= 256 columns), n <= 128.
+ * 0 = none; 1 = both, lockstep kernel; 2 = both, warp-specialised kernel; 3 (default) = the measured winner per product:
+ * X^T*G on the warp-specialised kernel, X*W on cuBLAS.  Also GNNA_TC_GEMM in the environment.  Returns the previous mode. */
 GNNA_API int gnna_set_tc_gemm(int mode);
 
 /* 1 = use the persistent kernel that streams the group table and the column indices through TMA bulk copies

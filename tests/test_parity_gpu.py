@@ -811,7 +811,8 @@ def _sgemm(A, B, ta=False):
 
 @pytest.fixture(params=[1, 2], ids=["lockstep", "warp-specialised"])
 def tc_gemm(request):
-    """The tensor-core products are opt-in (GNNA_TC_GEMM / gnna_set_tc_gemm): 1 = lockstep kernel, 2 = warp-specialised."""
+    """Force both tall-skinny products onto the tensor cores (GNNA_TC_GEMM / gnna_set_tc_gemm): 1 = lockstep kernel,
+    2 = warp-specialised (the default mode 3 uses it for X^T*G only)."""
     from gnnadvisor_osdi21_b200 import _lib
     prev = _lib.set_tc_gemm(request.param)
     yield request.param
