@@ -861,6 +861,21 @@ def test_tensor_core_gemm_tn_is_fp32_grade(rows, m, n, tc_gemm):
     assert float(((C.double() - ref).abs() / terms).max()) <= 4e-6
 
 
+def test_default_product_routing():
+    """Default mode 3: X^T*G runs on the warp-specialised tcgen05 kernel (one launch of ours), X*W on cuBLAS (none)."""
+    from gnnadvisor_osdi21_b200 import _lib
+    assert _lib.set_tc_gemm(3) == 3
+    X, W, G = torch.randn(12000, 602, device=DEV), torch.randn(602, 64, device=DEV), torch.randn(12000, 64, device=DEV)
+    _lib.launch_count(reset=True)
+    C = _sgemm(X, G, ta=True)
+    assert _lib.launch_count() == 1
+    terms = X.abs().double().t() @ G.abs().double()
+    assert float(((C.double() - X.double().t() @ G.double()).abs() / terms).max()) <= 4e-6
+    _lib.launch_count(reset=True)
+    _sgemm(X, W)
+    assert _lib.launch_count() == 0
+
+
 def test_small_or_odd_products_stay_on_cublas(tc_gemm):
     from gnnadvisor_osdi21_b200 import _lib
     A, B = torch.randn(500, 48, device=DEV), torch.randn(48, 16, device=DEV)
