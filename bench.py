@@ -96,7 +96,7 @@ def l2_peak_gbs(device=None):
     return res
 
 
-def roofline_of(B, kernel_ms, feature_bytes, kernel, note="", traffic=None, traffic_source=None, **extra):
+def roofline_of(B, kernel_ms, feature_bytes, kernel, note="", traffic=None, traffic_source=None, l2_port_pct=None, **extra):
     """The roofline object of one aggregation launch.  B = algorithmic bytes of the launch (alg_bytes), kernel_ms = its
     live CUDA-event time.  The roof depends on where the gathered matrix lives: when it fits in L2 (feature_bytes < 60 % of
     the L2) every neighbour-row read is an L2 hit and the bound is the L2 -> SM path, whose peak is measured on this box
@@ -117,6 +117,11 @@ def roofline_of(B, kernel_ms, feature_bytes, kernel, note="", traffic=None, traf
          "gathered_matrix_MB": feature_bytes / 1e6,
          "l2_probe": l2,
          "frac_of_random_row_l2_rate": achieved / l2["rows256_GBs"],
+         # the hardware-counter view of the same kernel (committed ncu capture): share of the L2 -> crossbar port's peak cycles.
+         # The probe above reaches only ~55 % of that port where the gather reaches 86.6 %, so `peak` is a LOWER bound of the
+         # roof and frac may exceed 1; achieved / (this share) is the roof the counter implies
+         "l2_port_pct_of_peak_ncu": l2_port_pct,
+         "l2_roof_implied_by_ncu_GBs": (achieved / (l2_port_pct / 100.0)) if (l2_port_pct and l2_resident) else None,
          "hbm": {"achieved": achieved, "peak": hbm_peak, "frac": achieved / hbm_peak, "peak_source": hbm_src,
                  "dram_GBs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None,
                  "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None},
@@ -127,13 +132,14 @@ def roofline_of(B, kernel_ms, feature_bytes, kernel, note="", traffic=None, traf
 
 def committed_traffic(key):
     """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of a kernel capture committed under profiles/
-    (profiles/dram_traffic.json: value + the capture file it was read from), or (None, None)."""
+    (profiles/dram_traffic.json: value + the capture file it was read from) and the capture's L2-port share:
+    (bytes, source, l2_port_pct) or (None, None, None)."""
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
     try:
         prof = json.load(open(tp))
-        return prof.get(key), prof.get(key + "_source")
+        return prof.get(key), prof.get(key + "_source"), prof.get(key + "_l2_port_pct")
     except Exception:   # noqa: BLE001
-        return None, None
+        return None, None, None
 
 
 def alg_bytes(E, N, D, P, sx=4, sy=4, gcn=False, prescale=False):
@@ -394,9 +400,9 @@ def run_single(args):
     peak, peak_src = peak_gbs()
     B = alg_bytes(E, N, D, P)                      # one launch of the gather (the pre-scale pass is another kernel)
     B_step = alg_bytes(E, N, D, P, prescale=True)
-    traffic, traffic_src = committed_traffic("%s_D%d_f32" % (args.workload, D)) if args.scale == 1.0 else (None, None)
+    traffic, traffic_src, port_pct = committed_traffic("%s_D%d_f32" % (args.workload, D)) if args.scale == 1.0 else (None, None, None)
     roofline = roofline_of(
-        B, kernel_ms, N * D * 4, traffic=traffic, traffic_source=traffic_src,
+        B, kernel_ms, N * D * 4, traffic=traffic, traffic_source=traffic_src, l2_port_pct=port_pct,
         kernel="gnna::aggregate_kernel<float,4,16,1,false> (+ prescale_rows_kernel<4>, 0.4% of the bytes)",
         note="achieved = alg_bytes_per_launch / kernel_ms, kernel_ms = the aggregate kernel alone timed live with CUDA events (one launch "
              "per call); the step (ms_per_step) = cudaMemsetAsync(out) + prescale_rows + that kernel.  bound = l2 when the gathered "
@@ -576,8 +582,8 @@ def hbm_bound_leg(args, device):
                                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "aggregate (kernel only)")
     k = max(5, min(args.steps, 30))
     kernel_ms = timed(kernel_only, k, 3) / k
-    traffic, src = committed_traffic("ogbn-products_D64_f32")
-    r = roofline_of(alg_bytes(E, N, D, P), kernel_ms, N * D * 4, traffic=traffic, traffic_source=src,
+    traffic, src, port_pct = committed_traffic("ogbn-products_D64_f32")
+    r = roofline_of(alg_bytes(E, N, D, P), kernel_ms, N * D * 4, traffic=traffic, traffic_source=src, l2_port_pct=port_pct,
                     kernel="gnna::aggregate_kernel<float,4,16,1,false>",
                     note="L2 absorbs the hub rows, so DRAM traffic (hbm.dram_GBs, from the committed ncu capture) is below the "
                          "algorithmic bytes; hbm.dram_frac is the fraction of the measured copy peak the kernel really draws")
