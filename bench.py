@@ -85,13 +85,20 @@ def l2_peak_gbs(device=None):
         sink = torch.zeros(1, dtype=torch.int32, device=device)
         res = {"buffer_MB_at_most": nbytes >> 20, "passes": passes, "l2_size_MB": torch.cuda.get_device_properties(device).L2_cache_size / 2 ** 20}
         for name, mode in (("seq", 0), ("rows256", 1)):
-            per_pass = ctypes.c_int64(0)
+            best_rate, best_block = 0.0, None
+            for block in (128, 256, 512):          # the same 1536 threads per SM in CTAs of three sizes: the best one is the roof
+                per_pass = ctypes.c_int64(0)
 
-            def run():
-                _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), nbytes, passes, mode, 3, ctypes.c_void_p(sink.data_ptr()),
-                                                  ctypes.byref(per_pass), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2 probe")
-            best = min(timed(run, 1, 1) for _ in range(5))
-            res[name + "_GBs"] = per_pass.value * passes / (best * 1e-3) / 1e9
+                def run():
+                    _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), nbytes, passes, mode, 1536, block,
+                                                      ctypes.c_void_p(sink.data_ptr()), ctypes.byref(per_pass),
+                                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2 probe")
+                t = min(timed(run, 1, 1) for _ in range(4))
+                rate = per_pass.value * passes / (t * 1e-3) / 1e9
+                res["%s_block%d_GBs" % (name, block)] = rate
+                if rate > best_rate:
+                    best_rate, best_block = rate, block
+            res[name + "_GBs"], res[name + "_block"] = best_rate, best_block
     _L2_PEAK[device.index] = res
     return res
 

@@ -84,7 +84,7 @@ SIGNATURES = {
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
     "gnna_stream_pairs": (i32, [i64, i64, ctypes.c_uint64, i64, i32, i32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "gnna_probe_l2_read": (i32, [ctypes.c_void_p, i64, i32, i32, i32, ctypes.c_void_p, ctypes.POINTER(i64), ctypes.c_void_p]),
+    "gnna_probe_l2_read": (i32, [ctypes.c_void_p, i64, i32, i32, i32, i32, ctypes.c_void_p, ctypes.POINTER(i64), ctypes.c_void_p]),
     "gnna_launch_count": (i64, [i32]),
     "gnna_set_gcn_exact": (i32, [i32]),
     "gnna_set_tc_gemm": (i32, [i32]),

@@ -24,7 +24,7 @@ constexpr int PROBE_UNROLL = 8;
 // size down), so every thread issues only full batches of PROBE_UNROLL independent loads -- no serialised tail -- and in
 // mode 0 every chunk of the buffer is loaded exactly once per pass.  The buffer is ~100x an SM's L1 and a CTA reads a
 // different slice in every pass, so every load is served by L2.
-__global__ void __launch_bounds__(512, 3)
+__global__ void __launch_bounds__(512, 3)   // <= 42 registers: 1536 threads per SM at any block size
 l2_read_probe_kernel(const uint4 *__restrict__ buf, long long n16, int passes, int mode, unsigned *sink)
 {
     const long long T = (long long)gridDim.x * blockDim.x;
@@ -65,11 +65,12 @@ l2_read_probe_kernel(const uint4 *__restrict__ buf, long long n16, int passes, i
 
 // Reads `buf` `passes` times.  mode 0: coalesced stream, 1: random 256-byte rows.  `bytes` is rounded DOWN to a whole number
 // of batches (SMs * ctas_per_sm * 512 threads * 8 loads * 16 bytes); the bytes one pass really reads come back in
-// *bytes_per_pass.  ctas_per_sm <= 0 picks 3 (1536 threads per SM, 8 loads of 16 bytes in flight each: 196 KB per SM, what the
-// gather keeps in flight with 48 resident warps).
+// *bytes_per_pass.  threads_per_sm <= 0 picks 1536 (8 loads of 16 bytes in flight each: 196 KB per SM, what the gather keeps in
+// flight with 48 resident warps); block_threads (128, 256 or 512; <= 0 picks 512) is the CTA size they come in -- the gather
+// runs 128-thread CTAs, and small CTAs drift apart instead of issuing their batches in lockstep.
 // `sink` is any 4 writable bytes of device memory.
-extern "C" int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, int mode, int ctas_per_sm, void *sink,
-                                  int64_t *bytes_per_pass, void *stream)
+extern "C" int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, int mode, int threads_per_sm, int block_threads,
+                                  void *sink, int64_t *bytes_per_pass, void *stream)
 {
     using namespace gnna;
     GNNA_REQUIRE(buf && sink && passes > 0 && (mode == 0 || mode == 1), "gnna_probe_l2_read: bad argument");
@@ -77,12 +78,15 @@ extern "C" int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, in
     int dev = 0, sms = 148;
     GNNA_CUDA_CHECK(cudaGetDevice(&dev));
     GNNA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (ctas_per_sm <= 0) ctas_per_sm = 3;
-    const long long batch16 = (long long)sms * ctas_per_sm * 512 * PROBE_UNROLL;      // chunks per full batch of the grid
+    if (threads_per_sm <= 0) threads_per_sm = 1536;
+    if (block_threads <= 0) block_threads = 512;
+    GNNA_REQUIRE(block_threads == 128 || block_threads == 256 || block_threads == 512, "gnna_probe_l2_read: block_threads must be 128, 256 or 512");
+    const int ctas_per_sm = threads_per_sm / block_threads > 0 ? threads_per_sm / block_threads : 1;
+    const long long batch16 = (long long)sms * ctas_per_sm * block_threads * PROBE_UNROLL;      // chunks per full batch of the grid
     const long long n16 = (bytes / 16) / batch16 * batch16;
     GNNA_REQUIRE(n16 > 0, "gnna_probe_l2_read: buffer smaller than one batch (%lld bytes)", batch16 * 16);
     if (bytes_per_pass) *bytes_per_pass = n16 * 16;
-    l2_read_probe_kernel<<<sms * ctas_per_sm, 512, 0, (cudaStream_t)stream>>>((const uint4 *)buf, n16, passes, mode, (unsigned *)sink);
+    l2_read_probe_kernel<<<sms * ctas_per_sm, block_threads, 0, (cudaStream_t)stream>>>((const uint4 *)buf, n16, passes, mode, (unsigned *)sink);
     GNNA_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
     return GNNA_OK;

@@ -317,10 +317,10 @@ GNNA_API int gnna_stream_pairs(int64_t start, int64_t count, uint64_t seed_mix, 
 /* Measurement infrastructure: read `bytes` of `buf` (a buffer that fits in L2) `passes` times with 128-bit loads that
  * bypass L1 -- mode 0 a coalesced stream, mode 1 randomly ordered 256-byte rows (the D=64 fp32 gather's pattern).  Timed
  * by the caller with CUDA events, it gives bench.py the L2 -> SM bandwidth of the box: the roof of the aggregation when
- * the feature matrix is L2-resident.  `bytes` is rounded down to whole batches of the grid; *bytes_per_pass = what one pass
- * reads.  `sink`: any 4 writable device bytes.  No reference counterpart.                                       */
-GNNA_API int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, int mode, int ctas_per_sm, void *sink,
-                                int64_t *bytes_per_pass, void *stream);
+ * the feature matrix is L2-resident.  threads_per_sm (<= 0: 1536) come in CTAs of block_threads (128 / 256 / 512).  `bytes` is
+ * rounded down to whole batches of the grid; *bytes_per_pass = what one pass reads.  `sink`: any 4 writable device bytes.  No reference counterpart.                                       */
+GNNA_API int gnna_probe_l2_read(const void *buf, int64_t bytes, int passes, int mode, int threads_per_sm, int block_threads,
+                                void *sink, int64_t *bytes_per_pass, void *stream);
 
 /* GCN rounding: 0 (default) = out_i = n_i * sum_j (n_j * x_j): one pre-scale pass over the features,
  * then a weight-free gather (no per-edge degrees[nid] gather; each term within 2 roundings of the

@@ -54,7 +54,7 @@ buf = torch.zeros(30 << 18, device=dev)
 sink = torch.zeros(1, dtype=torch.int32, device=dev)
 per = ctypes.c_int64(0)
 for mode in (0, 0, 1):
-    _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), 30 << 20, 8, mode, 3, ctypes.c_void_p(sink.data_ptr()),
+    _lib.check(lib.gnna_probe_l2_read(ctypes.c_void_p(buf.data_ptr()), 30 << 20, 8, mode, 1536, 128, ctypes.c_void_p(sink.data_ptr()),
                                       ctypes.byref(per), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "probe")
 torch.cuda.synchronize()
 print("done", wl, D)
