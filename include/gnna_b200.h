@@ -253,15 +253,6 @@ GNNA_API int gnna_ipc_open(const unsigned char *handle64, void **ptr);
 GNNA_API int gnna_ipc_close(void *ptr);
 GNNA_API int gnna_ipc_free(void *ptr);
 
-/* gnna_halo_push_f32 for DENSE halos: a peer whose bit (by rank) is set in dense_mask asked for ALL n_local rows of this
- * rank (its block for this rank is the rank's local rows as they lie in memory) and gets them as ONE device-to-device
- * cudaMemcpyAsync over NVLink on the copy engines -- no SM, no index list; peers not in the mask are served by the push
- * kernel from their send lists.  Same flags / acknowledgements / step counter as gnna_halo_push_f32.          */
-GNNA_API int gnna_halo_push_ce(const float *x_local, int64_t n_local, const int64_t *send_idx, const int32_t *send_begin_host,
-                               void *const *peer_feature_base_host, void *const *peer_ctrl_host,
-                               const int64_t *peer_dst_row0_host, void *my_ctrl,
-                               int world, int my_rank, int dim, uint32_t dense_mask, void *stream);
-
 /* One exchange step = begin_step, push, wait, (aggregate), ack.  The step number (1, 2, 3, ...) lives in the
  * control block and is read on the device, so a step captured in a CUDA graph can be replayed.
  * begin_step: first thing on the compute stream: step += 1.
@@ -280,6 +271,15 @@ GNNA_API int gnna_halo_push_f32(const float *x_local, const int64_t *send_idx, c
                                 void *const *peer_feature_base_host, void *const *peer_ctrl_host,
                                 const int64_t *peer_dst_row0_host, void *my_ctrl,
                                 int world, int my_rank, int dim, void *stream);
+
+/* gnna_halo_push_f32 for DENSE halos: a peer whose bit (by rank) is set in dense_mask asked for ALL n_local rows of this
+ * rank (its block for this rank is the rank's local rows as they lie in memory) and gets them as ONE device-to-device
+ * cudaMemcpyAsync over NVLink on the copy engines -- no SM, no index list; peers not in the mask are served by the push
+ * kernel from their send lists.  Same flags / acknowledgements / step counter as gnna_halo_push_f32.          */
+GNNA_API int gnna_halo_push_ce(const float *x_local, int64_t n_local, const int64_t *send_idx, const int32_t *send_begin_host,
+                               void *const *peer_feature_base_host, void *const *peer_ctrl_host,
+                               const int64_t *peer_dst_row0_host, void *my_ctrl,
+                               int world, int my_rank, int dim, uint32_t dense_mask, void *stream);
 GNNA_API int gnna_halo_wait(void *my_ctrl, int world, int my_rank, uint32_t peer_mask, void *stream);
 GNNA_API int gnna_halo_ack(void *const *peer_ctrl_host, void *my_ctrl, int world, int my_rank, void *stream);
 
