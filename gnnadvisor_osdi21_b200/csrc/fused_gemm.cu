@@ -30,6 +30,9 @@
 
 namespace gnna {
 
+#ifndef GNNA_FUSED_MIN_CTAS
+#define GNNA_FUSED_MIN_CTAS 2     // CTAs of 512 threads per SM the register budget is set for (2: 64 registers, 3: 40)
+#endif
 constexpr int TILE_M = 128;
 constexpr int FUSED_THREADS = 512;   // 16 warps; 2 CTAs per SM (64-register budget) keep 32 warps gathering
 
@@ -68,8 +71,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// First index of the sorted array a[0..n) whose value is >= key, found by ONE WARP: 32 probes per round trip, so a table
+// of 3.7 M groups takes 5 dependent loads instead of the 22 of a binary search (the tile's CTA waits for this).
+__device__ __forceinline__ long long warp_lower_bound(const int32_t *__restrict__ a, long long n, long long key, int lane)
+{
+    long long lo = 0, hi = n;                              // the answer lies in [lo, hi]
+    while (hi > lo) {
+        const long long step = (hi - lo + 31) / 32;        // >= 1
+        const long long pos = lo + (long long)lane * step;
+        const bool ge = (pos >= hi) || ((long long)__ldg(a + pos) >= key);
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (m == 0) { lo += 31 * step + 1; continue; }     // every probe is below the key
+        const int f = __ffs(m) - 1;                        // first probe at or above the key
+        const long long at = lo + (long long)f * step;
+        hi = at < hi ? at : hi;
+        if (f > 0) lo += (long long)(f - 1) * step + 1;    // the probe before it was below
+        else hi = lo;
+    }
+    return lo;
+}
+
 template <typename T, int DIN>
-__global__ void __launch_bounds__(FUSED_THREADS, 2)
+__global__ void __launch_bounds__(FUSED_THREADS, GNNA_FUSED_MIN_CTAS)
 fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W, float *__restrict__ out,
                             float *__restrict__ x_agg, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                             const float *__restrict__ degrees, const int32_t *__restrict__ part_ptr,
@@ -101,17 +124,11 @@ fused_aggregate_gemm_kernel(const T *__restrict__ X, const float *__restrict__ W
     const long long row0 = (long long)blockIdx.x * TILE_M;
 
     // ---- setup: group range of this tile, TMEM, barrier, B operand, zero the fp32 tile
+    if (warp == 1 || warp == 2) {              // first group whose node >= row0 / >= row0 + TILE_M: two warps, side by side
+        const long long v = warp_lower_bound(part2node, num_parts, warp == 1 ? row0 : row0 + TILE_M, lane);
+        if (lane == 0) s_range[warp - 1] = v;
+    }
     if (tid == 0) {
-        auto lower = [&](long long key) {      // first group whose node >= key
-            long long lo = 0, hi = num_parts;
-            while (lo < hi) {
-                long long mid = (lo + hi) >> 1;
-                if ((long long)__ldg(part2node + mid) < key) lo = mid + 1; else hi = mid;
-            }
-            return lo;
-        };
-        s_range[0] = lower(row0);
-        s_range[1] = lower(row0 + TILE_M);
         s_range[2] = (long long)__ldg(row_ptr + num_nodes);   // entries of col_idx: bound of the speculative id prefetch
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
