@@ -81,6 +81,10 @@ SIGNATURES = {
     "gnna_halo_wait": (i32, [ctypes.c_void_p, i32, i32, ctypes.c_uint32, ctypes.c_void_p]),
     "gnna_halo_ack": (i32, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, i32, i32, ctypes.c_void_p]),
     "gnna_rabbit_reorder_host": (i32, [c_i32p, c_i32p, i64, i64, c_i32p]),
+    "gnna_rabbit_reorder_host_ex": (i32, [c_i32p, c_i32p, i64, i64, c_i32p, i64]),
+    "gnna_edge_text_scan": (i32, [ctypes.c_char_p, ctypes.POINTER(i64)]),
+    "gnna_edge_text_parse": (i32, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
+    "gnna_csr_from_edges_host": (i32, [ctypes.c_void_p, ctypes.c_void_p, i64, i64, c_i32p, c_i32p, ctypes.POINTER(i64)]),
     "gnna_query_launch": (i32, [i32, i32, i64, i32, i32, ctypes.POINTER(LaunchInfo)]),
     "gnna_stream_pairs": (i32, [i64, i64, ctypes.c_uint64, i64, i32, i32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

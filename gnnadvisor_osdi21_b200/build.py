@@ -12,7 +12,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libgnna_b200.so")
-SOURCES = ["aggregate.cu", "build_part.cu", "ops.cu", "reorder.cu", "halo.cu", "fused_gemm.cu", "aggregate_staged.cu", "aggregate_runs.cu", "probe.cu", "aggregate_small.cu", "graphgen.cu", "gemm_tf32x3.cu"]
+SOURCES = ["aggregate.cu", "build_part.cu", "ops.cu", "reorder.cu", "halo.cu", "fused_gemm.cu", "aggregate_staged.cu", "aggregate_runs.cu", "probe.cu", "aggregate_small.cu", "graphgen.cu", "gemm_tf32x3.cu", "dataset.cu"]
 HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "gather.cuh"), os.path.join(PKG, "..", "include", "gnna_b200.h")]
 
 NVCC_FLAGS = [

@@ -11,16 +11,30 @@
 //      edges are folded into `u`'s lazily, the next time `u` itself is visited;
 //   3. new ids = depth-first walk of every top-level community's merge tree, communities laid out one
 //      after the other, so vertices merged together get adjacent ids.
-// The reference runs step 2 with optimistic parallel merges, so its permutation differs from run to run
-// and no test pins it; this implementation is sequential and deterministic.  What is
-// checked: the result is a permutation, applied consistently, and it shortens the average edge span
-// of graphs with community structure (tests/test_reorder.py).
+//
+// Parallelism.  The reference runs step 2 with optimistic merges under compare-and-swap (:477-526): fast, but
+// its permutation differs from run to run and no test can pin it.  Here step 2 is parallel AND
+// deterministic: the degree-ordered vertex list is cut into WINDOWS; all host threads fold the edges of a
+// window's vertices and pick their best neighbour against the state at the start of the window (the expensive
+// part: every edge is traced to its community, sorted and summed), then the window's merges are applied one
+// after the other in list order (a few stores per vertex).  A vertex whose choice meanwhile joined the vertex
+// itself is carried into the next window (the counterpart of the reference's `pends`).  The result depends on
+// the window length only -- never on the number of threads or their timing -- and a window of 1 IS the
+// sequential algorithm (GNNA_RABBIT_WINDOW=1).  Step 1 is parallel sorts plus per-vertex folding, step 3 a
+// linear walk.
+// What is checked: the result is a permutation, applied consistently, identical from run to run and for any
+// thread count, and it shortens the average edge span of graphs with community structure as well as the
+// sequential order does (tests/test_reorder.py).
 #include <algorithm>
 #include <parallel/algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <numeric>
 #include <utility>
 #include <vector>
+
+#include <omp.h>
 
 #include "common.h"
 
@@ -36,14 +50,16 @@ struct Dendrogram {
     double tot_wgt = 0.0;
 };
 
+// Root of v's community.  Called concurrently while a window is evaluated: `com` only changes between windows, so every
+// thread finds the same root; the compressing stores write ancestors of the entry they replace (relaxed atomics: any
+// interleaving leaves a valid, shorter path).
 inline int32_t trace_com(Dendrogram &g, int32_t v)
 {
-    int32_t r = v;
-    while (g.com[r] != r) r = g.com[r];
-    while (g.com[v] != r) {                // path compression
-        int32_t nx = g.com[v];
-        g.com[v] = r;
-        v = nx;
+    int32_t r = v, p;
+    while ((p = __atomic_load_n(&g.com[r], __ATOMIC_RELAXED)) != r) r = p;
+    while ((p = __atomic_load_n(&g.com[v], __ATOMIC_RELAXED)) != r) {
+        __atomic_store_n(&g.com[v], r, __ATOMIC_RELAXED);
+        v = p;
     }
     return r;
 }
@@ -62,6 +78,7 @@ void compact(std::vector<WEdge> &e)
 }
 
 // fold the edges of v and of every community merged into v since the last visit into es[v]
+// (only v's own data and its children's edge lists are written: vertices of one window never share those)
 void unite(Dendrogram &g, int32_t v, std::vector<WEdge> &buf)
 {
     buf.clear();
@@ -79,16 +96,48 @@ void unite(Dendrogram &g, int32_t v, std::vector<WEdge> &buf)
     g.es[v].assign(buf.begin(), buf.end());
 }
 
+// neighbour community with the largest positive modularity gain, or v itself (rabbit_order.hpp:455-467)
+inline int32_t find_best(const Dendrogram &g, int32_t v)
+{
+    const double vstr = g.str[v];
+    double best_gain = 0.0;
+    int32_t best = v;
+    for (const WEdge &e : g.es[v]) {
+        const double gain = (double)e.second - vstr * g.str[e.first] / g.tot_wgt;
+        if (gain > best_gain) { best_gain = gain; best = e.first; }
+    }
+    return best;
+}
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 }  // namespace
 
-extern "C" int gnna_rabbit_reorder_host(const int32_t *src, const int32_t *dst, int64_t num_edges,
-                                        int64_t num_nodes, int32_t *perm_old_to_new)
+// window <= 0: GNNA_RABBIT_WINDOW from the environment, else the built-in choice (a function of num_nodes only)
+extern "C" int gnna_rabbit_reorder_host_ex(const int32_t *src, const int32_t *dst, int64_t num_edges,
+                                           int64_t num_nodes, int32_t *perm_old_to_new, int64_t window)
 {
     GNNA_REQUIRE(num_nodes >= 0 && num_edges >= 0, "rabbit_reorder: negative size");
     GNNA_REQUIRE(num_nodes < 0x7fffffffLL, "rabbit_reorder: too many vertices");
     if (num_nodes == 0) return GNNA_OK;
     GNNA_REQUIRE(perm_old_to_new && (num_edges == 0 || (src && dst)), "rabbit_reorder: null pointer");
     const int32_t n = (int32_t)num_nodes;
+    const bool verbose = getenv("GNNA_RABBIT_VERBOSE") != nullptr;
+    double t_mark = now_s();
+    auto lap = [&](const char *what) {
+        if (!verbose) return;
+        const double t = now_s();
+        fprintf(stderr, "[rabbit] %-28s %8.3f s\n", what, t - t_mark);
+        t_mark = t;
+    };
+    if (window <= 0) {
+        const char *w = getenv("GNNA_RABBIT_WINDOW");
+        window = w ? atoll(w) : 0;
+    }
+    if (window <= 0) window = std::min<int64_t>(16384, std::max<int64_t>(1, num_nodes / 64));
 
     // 1. symmetric weighted adjacency, no self loops, duplicates merged
     // (the edge list passes are the bulk of the time at 10^8 edges: all host threads, as the reference's OpenMP build)
@@ -109,52 +158,107 @@ extern "C" int gnna_rabbit_reorder_host(const int32_t *src, const int32_t *dst, 
     }
     GNNA_REQUIRE(bad < 0, "rabbit_reorder: vertex id out of range at edge %lld", bad);
     __gnu_parallel::sort(keys.begin(), keys.end());
-    while (!keys.empty() && keys.back() == ~0ull) keys.pop_back();
+    const size_t nkeys = (size_t)(std::lower_bound(keys.begin(), keys.end(), ~0ull) - keys.begin());
+    lap("edge keys + sort");
     Dendrogram g;
     g.es.resize(n);
     g.com.resize(n);
-    std::iota(g.com.begin(), g.com.end(), 0);
     g.child.assign(n, -1);
     g.sibling.assign(n, -1);
     g.united_child.assign(n, -1);
     g.str.assign(n, 0.0);
-    for (size_t i = 0; i < keys.size();) {
-        size_t j = i;
-        while (j < keys.size() && keys[j] == keys[i]) j++;
-        const int32_t a = (int32_t)(keys[i] >> 32), b = (int32_t)(keys[i] & 0xffffffffu);
-        const float w = (float)(j - i);
-        g.es[a].push_back(WEdge(b, w));
-        g.str[a] += w;
-        g.tot_wgt += w;
-        i = j;
+    // first[v] = index of the first key whose source is >= v; every key that starts a new source fills its gap
+    std::vector<size_t> first((size_t)n + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)nkeys; i++) {
+        const int32_t a = (int32_t)(keys[i] >> 32);
+        const int32_t prev = i ? (int32_t)(keys[i - 1] >> 32) : -1;
+        for (int32_t v = prev + 1; v <= a; v++) first[v] = (size_t)i;
     }
+    {
+        const int32_t last = nkeys ? (int32_t)(keys[nkeys - 1] >> 32) : -1;
+        for (int32_t v = last + 1; v <= n; v++) first[v] = nkeys;
+    }
+    double tot = 0.0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : tot)
+    for (int32_t v = 0; v < n; v++) {
+        g.com[v] = v;
+        std::vector<WEdge> &e = g.es[v];
+        double s = 0.0;
+        for (size_t i = first[v]; i < first[v + 1];) {
+            size_t j = i;
+            while (j < first[v + 1] && keys[j] == keys[i]) j++;
+            e.push_back(WEdge((int32_t)(keys[i] & 0xffffffffu), (float)(j - i)));
+            s += (double)(j - i);
+            i = j;
+        }
+        g.str[v] = s;
+        tot += s;
+    }
+    g.tot_wgt = tot;
     std::vector<uint64_t>().swap(keys);
+    std::vector<size_t>().swap(first);
+    lap("adjacency");
 
-    // 2. incremental aggregation in ascending (unweighted) degree order
+    // 2. incremental aggregation in ascending (unweighted) degree order, window by window
     std::vector<int32_t> order(n);
     std::iota(order.begin(), order.end(), 0);
     __gnu_parallel::stable_sort(order.begin(), order.end(),
                                 [&](int32_t a, int32_t b) { return g.es[a].size() < g.es[b].size(); });
+    lap("degree order");
     std::vector<int32_t> tops;
-    std::vector<WEdge> buf;
-    for (int32_t v : order) {
-        unite(g, v, buf);
-        const double vstr = g.str[v];
-        double best_gain = 0.0;
-        int32_t best = v;
-        for (const WEdge &e : g.es[v]) {
-            const double gain = (double)e.second - vstr * g.str[e.first] / g.tot_wgt;
-            if (gain > best_gain) { best_gain = gain; best = e.first; }
-        }
-        if (best == v) {
-            tops.push_back(v);
-        } else {                           // v joins best: hang it under best, newest child first
-            g.str[best] += vstr;
+    std::vector<int32_t> win, carried, cand;
+    win.reserve((size_t)window * 2);
+    long long n_windows = 0, n_carried = 0;
+    if (window == 1) {                     // the sequential algorithm, without the window machinery
+        std::vector<WEdge> buf;
+        for (int32_t v : order) {
+            unite(g, v, buf);
+            const int32_t best = find_best(g, v);
+            if (best == v) { tops.push_back(v); continue; }
+            g.str[best] += g.str[v];       // v joins best: hang it under best, newest child first
             g.sibling[v] = g.child[best];
             g.child[best] = v;
             g.com[v] = best;
         }
+    } else {
+        const int threads = std::max(1, omp_get_max_threads());
+        std::vector<std::vector<WEdge>> bufs(threads);
+        size_t next = 0;
+        while (next < (size_t)n || !carried.empty()) {
+            win.assign(carried.begin(), carried.end());       // carried vertices keep their place at the front
+            carried.clear();
+            while (next < (size_t)n && (int64_t)win.size() < window) win.push_back(order[next++]);
+            const int64_t wn = (int64_t)win.size();
+            cand.resize((size_t)wn);
+            // (a) every thread: fold and choose against the state at the start of the window
+            // (a short window is not worth waking the team for: same result, the calling thread does it)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads) if (wn >= 256)
+            for (int64_t i = 0; i < wn; i++) {
+                unite(g, win[i], bufs[omp_get_thread_num()]);
+                cand[i] = find_best(g, win[i]);
+            }
+            // (b) in list order: apply
+            for (int64_t i = 0; i < wn; i++) {
+                const int32_t v = win[i];
+                if (cand[i] == v) { tops.push_back(v); continue; }
+                const int32_t r = trace_com(g, cand[i]);       // the choice may have joined a community in this window
+                if (r == v) {                                   // ... v's own: look again with its edges folded in
+                    carried.push_back(v);
+                    n_carried++;
+                    continue;
+                }
+                g.str[r] += g.str[v];
+                g.sibling[v] = g.child[r];
+                g.child[r] = v;
+                g.com[v] = r;
+            }
+            n_windows++;
+        }
     }
+    if (verbose) fprintf(stderr, "[rabbit] window %lld: %lld windows, %lld vertices carried over, %zu top-level communities\n",
+                         (long long)window, n_windows, n_carried, tops.size());
+    lap("aggregation");
 
     // 3. depth-first numbering of the merge trees, one top-level community after the other
     int32_t next_id = 0;
@@ -171,6 +275,13 @@ extern "C" int gnna_rabbit_reorder_host(const int32_t *src, const int32_t *dst, 
             if (g.sibling[v] != -1) push_chain(g.sibling[v]);
         }
     }
+    lap("numbering");
     GNNA_REQUIRE(next_id == n, "rabbit_reorder: internal error, numbered %d of %d vertices", next_id, n);
     return GNNA_OK;
+}
+
+extern "C" int gnna_rabbit_reorder_host(const int32_t *src, const int32_t *dst, int64_t num_edges,
+                                        int64_t num_nodes, int32_t *perm_old_to_new)
+{
+    return gnna_rabbit_reorder_host_ex(src, dst, num_edges, num_nodes, perm_old_to_new, 0);
 }

@@ -15,14 +15,21 @@ import torch
 
 
 # ------------------------------------------------------------------------------------------ CSR
-def csr_from_edges(src, dst, num_nodes):
+def csr_from_edges(src, dst, num_nodes, native=None):
     """(row_ptr int32 [N+1], col_idx int32 [E]) with duplicates merged and columns sorted, on the
-    device `src` lives on.  Equivalent to scipy coo_matrix((1,(src,dst))).tocsr() (dataset.py:110-111)."""
+    device `src` lives on.  Equivalent to scipy coo_matrix((1,(src,dst))).tocsr() (dataset.py:110-111).
+    native: host edge lists go through the multi-threaded builder of libgnna_b200.so (None: yes unless
+    GNNA_CSR_NATIVE=0); False keeps the torch ops -- what the synthetic generator uses, so bench.py's CPU reference arm
+    never loads the product's library."""
     src = torch.as_tensor(src).to(torch.int64).reshape(-1)
     dst = torch.as_tensor(dst).to(torch.int64).reshape(-1)
     num_nodes = int(num_nodes)
     if src.numel() != dst.numel():
         raise ValueError("src and dst differ in length (%d vs %d)" % (src.numel(), dst.numel()))
+    if native is None:
+        native = os.environ.get("GNNA_CSR_NATIVE", "1") == "1"
+    if native and src.device.type == "cpu":
+        return _csr_from_edges_native(src, dst, num_nodes)
     if src.numel() and (int(torch.minimum(src.min(), dst.min())) < 0 or int(torch.maximum(src.max(), dst.max())) >= num_nodes):
         # scipy's coo_matrix raises here too ("row index exceeds matrix dimensions"); without the check an id
         # >= num_nodes would alias into another row of the src*N+dst key
@@ -36,6 +43,23 @@ def csr_from_edges(src, dst, num_nodes):
     if int(row_ptr[-1]) >= 2 ** 31:
         raise ValueError("graph has %d edges; the int32 CSR contract of the reference stops at 2^31-1" % int(row_ptr[-1]))
     return row_ptr.to(torch.int32), cols
+
+
+def _csr_from_edges_native(src, dst, num_nodes):
+    """Host edge lists: the bucketed multi-threaded builder of libgnna_b200.so (csrc/dataset.cu) -- the same CSR bit for bit
+    (tests/test_graph.py compares both paths with scipy); GNNA_CSR_NATIVE=0 keeps the torch ops."""
+    import ctypes
+    from . import _lib
+    src, dst = src.contiguous(), dst.contiguous()
+    row_ptr = torch.empty(num_nodes + 1, dtype=torch.int32)
+    col = torch.empty(src.numel(), dtype=torch.int32)
+    nnz = ctypes.c_int64(0)
+    rc = _lib.load().gnna_csr_from_edges_host(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), src.numel(),
+                                              num_nodes, ctypes.c_void_p(row_ptr.data_ptr()), ctypes.c_void_p(col.data_ptr()),
+                                              ctypes.byref(nnz))
+    if rc != 0:
+        raise ValueError(_lib.load().gnna_last_error().decode())      # out-of-range endpoint / >= 2^31 edges, like the torch path
+    return row_ptr, col[:nnz.value].clone() if nnz.value < col.numel() else col
 
 
 def degrees_from_row_ptr_host(row_ptr):
@@ -162,7 +186,7 @@ def synth_graph(num_nodes, num_edges, kind="rmat", seed=20211, device="cpu", rma
         hi = torch.cat([hi, torch.tensor([N - 1], device=device)])
     src = torch.cat([lo, hi])
     dst = torch.cat([hi, lo])
-    return csr_from_edges(src, dst, N)
+    return csr_from_edges(src, dst, N, native=False)
 
 
 def stream_degree_estimate(num_nodes, num_pairs, kind="rmat", seed=20211, device="cpu", rmat=RMAT_DEFAULT,
@@ -307,16 +331,30 @@ def load_edge_file(path, text=None):
     if (text is None and path.endswith(".npz")) or text is False:
         obj = np.load(path)
         return obj["src_li"], obj["dst_li"], int(obj["num_nodes"])
-    src, dst = [], []
-    with open(path) as f:
-        for line in f:
-            parts = line.split()
-            if len(parts) >= 2 and not line.startswith(("#", "%")):
-                src.append(int(parts[0]))
-                dst.append(int(parts[1]))
-    src, dst = np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
-    n = int(max(src.max(), dst.max())) + 1 if len(src) else 0
-    return src, dst, n
+    return load_edge_text(path)
+
+
+def load_edge_text(path):
+    """Whitespace `src dst` text file -> (src int64, dst int64, num_nodes = largest id + 1), edges in file order
+    (dataset.py:62-72), parsed by all host threads in libgnna_b200.so (csrc/dataset.cu) instead of a Python loop over the
+    lines.  Blank lines and lines starting with '#' or '%' are skipped, tokens after the second ignored; any other line
+    that is not two integers raises ValueError with its line number (the reference's int()/unpack raises there too)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    cpath = os.fsencode(path)
+    cap = ctypes.c_int64(0)
+    if lib.gnna_edge_text_scan(cpath, ctypes.byref(cap)) != 0:
+        raise OSError(lib.gnna_last_error().decode())
+    src = np.empty(cap.value, dtype=np.int64)
+    dst = np.empty(cap.value, dtype=np.int64)
+    e, n = ctypes.c_int64(0), ctypes.c_int64(0)
+    if lib.gnna_edge_text_parse(cpath, ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(dst.ctypes.data), cap.value,
+                                ctypes.byref(e), ctypes.byref(n)) != 0:
+        raise ValueError(lib.gnna_last_error().decode())
+    if e.value < cap.value:                                   # comments / blank lines: give the slack back
+        src, dst = src[:e.value].copy(), dst[:e.value].copy()
+    return src, dst, int(n.value)
 
 
 def save_npz(path, src, dst, num_nodes):

@@ -11,8 +11,10 @@ import torch
 from . import _lib
 
 
-def permutation(edge_index, num_nodes=None):
-    """old id -> new id (int32 CPU tensor [num_nodes]) by Rabbit Order community renumbering."""
+def permutation(edge_index, num_nodes=None, window=0):
+    """old id -> new id (int32 CPU tensor [num_nodes]) by Rabbit Order community renumbering, on all host threads and
+    deterministic.  window: vertices evaluated concurrently against one state (csrc/reorder.cu); 1 = the sequential
+    algorithm, 0 = the library's choice."""
     e = torch.as_tensor(edge_index)
     if e.dim() != 2 or e.shape[0] != 2:
         raise RuntimeError("edge_index must have shape [2, E]")
@@ -20,7 +22,7 @@ def permutation(edge_index, num_nodes=None):
     n = int(num_nodes) if num_nodes is not None else (int(e.max()) + 1 if e.numel() else 0)
     perm = torch.empty(n, dtype=torch.int32)
     p = lambda t: ctypes.c_void_p(t.data_ptr() if t.numel() else 0)   # noqa: E731
-    _lib.check(_lib.load().gnna_rabbit_reorder_host(p(e[0]), p(e[1]), e.shape[1], n, p(perm)), "rabbit reorder")
+    _lib.check(_lib.load().gnna_rabbit_reorder_host_ex(p(e[0]), p(e[1]), e.shape[1], n, p(perm), int(window)), "rabbit reorder")
     return perm
 
 

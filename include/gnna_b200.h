@@ -285,11 +285,32 @@ GNNA_API int gnna_halo_ack(void *const *peer_ctrl_host, void *my_ctrl, int world
 
 /* ---- vertex reordering ----------------------------------------------------------------------
  * replaces the python module `rabbit` (rabbit_module/src/reorder.cpp:235-295, rabbit_order.hpp:393-673):
- * Rabbit Order community-based renumbering.  Host code, deterministic.  The edge list may be directed
- * and may contain duplicates and self loops (it is symmetrised internally, like the reference does).
- * perm_old_to_new_host[v] = new id of vertex v (a permutation of 0..num_nodes-1).               */
+ * Rabbit Order community-based renumbering.  Host code on all host threads, deterministic (the same permutation for
+ * any number of threads; the reference's optimistic parallel merges give a different one every run).  The edge list may
+ * be directed and may contain duplicates and self loops (it is symmetrised internally, like the reference does).
+ * perm_old_to_new_host[v] = new id of vertex v (a permutation of 0..num_nodes-1).
+ * _ex: `window` = vertices whose merges are evaluated concurrently against one state (csrc/reorder.cu); 1 = the
+ * sequential algorithm, <= 0 = GNNA_RABBIT_WINDOW or the built-in choice min(16384, num_nodes / 64).             */
 GNNA_API int gnna_rabbit_reorder_host(const int32_t *src_host, const int32_t *dst_host, int64_t num_edges,
                                       int64_t num_nodes, int32_t *perm_old_to_new_host);
+GNNA_API int gnna_rabbit_reorder_host_ex(const int32_t *src_host, const int32_t *dst_host, int64_t num_edges,
+                                         int64_t num_nodes, int32_t *perm_old_to_new_host, int64_t window);
+
+/* ---- dataset path on the host (csrc/dataset.cu) ------------------------------------------------
+ * replaces the loader of GNNAdvisor/dataset.py: the per-line Python loop over a whitespace `src dst` text file
+ * (:62-72) and scipy's coo_matrix(...).tocsr() (:108-111), both on all host threads.
+ * gnna_edge_text_scan: an upper bound of the number of edges in the file (its line count), to size the buffers.
+ * gnna_edge_text_parse: the edges in file order; lines that are blank or start with '#' / '%' are skipped, tokens after
+ * the second are ignored, anything else that is not two integers is an error naming the line (the reference raises
+ * ValueError); *num_nodes_host = largest id + 1 (:72).                                                              */
+GNNA_API int gnna_edge_text_scan(const char *path_host, int64_t *max_edges_host);
+GNNA_API int gnna_edge_text_parse(const char *path_host, int64_t *src_host, int64_t *dst_host, int64_t capacity,
+                                  int64_t *num_edges_host, int64_t *num_nodes_host);
+/* COO -> CSR exactly as scipy builds it for the reference (dataset.py:108-122): duplicate edges merged, the columns of a
+ * row ascending, self loops kept; an endpoint outside [0, num_nodes) is an error (scipy raises too).  row_ptr_host has
+ * num_nodes + 1 entries, col_idx_host room for num_edges; *nnz_host = edges left after merging (< 2^31).            */
+GNNA_API int gnna_csr_from_edges_host(const int64_t *src_host, const int64_t *dst_host, int64_t num_edges,
+                                      int64_t num_nodes, int32_t *row_ptr_host, int32_t *col_idx_host, int64_t *nnz_host);
 
 /* ---- introspection (for tests, bench.py and the tuner) ------------------------------------
  * Launch geometry the library would use for a given call: fills lanes_per_row, chunks_per_lane,

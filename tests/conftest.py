@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Host-side OpenMP regions (oracle, build_part, reorder, dataset path) are short and many; in a sandboxed container an
+# actively spinning team costs tens of milliseconds per region.  Must be set before any OpenMP runtime loads.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:

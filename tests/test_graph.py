@@ -23,21 +23,42 @@ def test_csr_from_edges_equals_scipy_coo_to_csr(n, e, seed):
     if e:
         src[: e // 4] = src[e // 4: 2 * (e // 4)]             # exact duplicates, self loops stay in
         dst[: e // 4] = dst[e // 4: 2 * (e // 4)]
-    rp, ci = graph.csr_from_edges(src, dst, n)
     erp, eci = _scipy_csr(src, dst, n)
-    assert rp.dtype == torch.int32 and ci.dtype == torch.int32
-    assert np.array_equal(rp.numpy(), erp) and np.array_equal(ci.numpy(), eci)
+    for native in (True, False):                               # csrc/dataset.cu on the host threads / torch ops
+        rp, ci = graph.csr_from_edges(src, dst, n, native=native)
+        assert rp.dtype == torch.int32 and ci.dtype == torch.int32
+        assert np.array_equal(rp.numpy(), erp) and np.array_equal(ci.numpy(), eci)
     # degrees: sqrt(max(deg, 1)) in float32 (dataset.py:11-18,121-122)
     deg = graph.degrees_from_row_ptr_host(rp).numpy()
     d = np.diff(erp).astype(np.float32)
     assert np.array_equal(deg, np.sqrt(np.maximum(d, 1).astype(np.float32)))
 
 
-def test_csr_from_edges_rejects_out_of_range_ids():
+def test_native_csr_builder_on_skewed_and_bucketed_inputs():
+    """Enough edges for several buckets and all host threads; a hub row that is most of one bucket; isolated rows at both
+    ends; every edge duplicated many times."""
+    rng = np.random.default_rng(11)
+    n, e = 70001, 400000
+    src = rng.integers(1, n - 1, e)
+    dst = rng.integers(1, n - 1, e)
+    src[:150000] = 4097                                        # hub
+    dst[150000:300000] = dst[:150000]
+    src[300000:] = src[299999]                                 # one row, random columns
+    src2, dst2 = np.concatenate([src, src[::-1]]), np.concatenate([dst, dst[::-1]])
+    rp, ci = graph.csr_from_edges(src2, dst2, n, native=True)
+    erp, eci = _scipy_csr(src2, dst2, n)
+    assert np.array_equal(rp.numpy(), erp) and np.array_equal(ci.numpy(), eci)
+    assert int(rp[1]) == 0 and int(rp[-1]) == int(rp[-2])      # rows 0 and n-1 are empty
+    one = graph.csr_from_edges([3], [3], 5, native=True)       # a single self loop stays in, like scipy keeps it
+    assert one[0].tolist() == [0, 0, 0, 0, 1, 1] and one[1].tolist() == [3]
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_csr_from_edges_rejects_out_of_range_ids(native):
     with pytest.raises(ValueError, match="outside"):
-        graph.csr_from_edges([0, 5], [1, 2], 5)               # scipy raises as well
+        graph.csr_from_edges([0, 5], [1, 2], 5, native=native)               # scipy raises as well
     with pytest.raises(ValueError, match="outside"):
-        graph.csr_from_edges([0, 1], [-1, 2], 5)
+        graph.csr_from_edges([0, 1], [-1, 2], 5, native=native)
     with pytest.raises(ValueError):
         sp.coo_matrix((np.ones(2), ([0, 5], [1, 2])), shape=(5, 5))
 
@@ -63,6 +84,66 @@ def test_custom_dataset_has_the_reference_constructor(tmp_path):
     assert np.array_equal(dt.column_index.numpy(), _scipy_csr(src, dst, dt.num_nodes)[1])
     with pytest.raises(ValueError, match=".npz"):
         graph.custom_dataset(txt, 16, 10, load_from_txt=False, device="cpu")
+
+
+def _reference_text_loop(path):
+    """dataset.py:62-72 as written: the per-line loop of the reference."""
+    src_li, dst_li, nodes = [], [], set()
+    with open(path) as fp:
+        for line in fp:
+            src, dst = line.strip('\n').split()
+            src, dst = int(src), int(dst)
+            src_li.append(src)
+            dst_li.append(dst)
+            nodes.add(src)
+            nodes.add(dst)
+    return np.asarray(src_li, dtype=np.int64), np.asarray(dst_li, dtype=np.int64), max(nodes) + 1
+
+
+def test_text_loader_equals_the_reference_loop(tmp_path):
+    rng = np.random.default_rng(5)
+    e = 300000                                                 # several MB: many pieces, all host threads
+    src, dst = rng.integers(0, 1 << 20, e), rng.integers(0, 977, e)
+    plain = str(tmp_path / "plain.txt")
+    with open(plain, "w") as f:
+        f.write("".join("%d %d\n" % (a, b) for a, b in zip(src, dst)))
+    s, d, n = graph.load_edge_text(plain)
+    rs, rd, rn = _reference_text_loop(plain)
+    assert s.dtype == np.int64 and np.array_equal(s, rs) and np.array_equal(d, rd) and n == rn
+    # what real files contain and the reference's loop also takes: tabs, several blanks, CRLF, no newline at the end
+    messy = str(tmp_path / "messy.txt")
+    with open(messy, "w", newline="") as f:
+        f.write("0\t5\n 7   2 \n3 4\r\n+6 1\n9 9")
+    s, d, n = graph.load_edge_text(messy)
+    rs, rd, rn = _reference_text_loop(messy)
+    assert s.tolist() == rs.tolist() == [0, 7, 3, 6, 9] and d.tolist() == rd.tolist() == [5, 2, 4, 1, 9] and n == rn == 10
+    # beyond the reference: comment lines, blank lines and a weight column are skipped / ignored
+    snap = str(tmp_path / "snap.txt")
+    with open(snap, "w") as f:
+        f.write("# Directed graph\n% mtx style\n\n1 2 0.5\n  \n2 0\n")
+    s, d, n = graph.load_edge_text(snap)
+    assert s.tolist() == [1, 2] and d.tolist() == [2, 0] and n == 3
+    empty = str(tmp_path / "empty.txt")
+    open(empty, "w").close()
+    s, d, n = graph.load_edge_text(empty)
+    assert len(s) == 0 and len(d) == 0 and n == 0
+
+
+@pytest.mark.parametrize("text,line", [("1 2\n3\n", 2), ("1 2\n3 4\nfoo bar\n", 3), ("1.5 2\n", 1), ("1 2x\n", 1),
+                                       ("1 99999999999999999999\n", 1)])
+def test_text_loader_names_the_malformed_line(tmp_path, text, line):
+    path = str(tmp_path / "bad.txt")
+    with open(path, "w") as f:
+        f.write(text)
+    with pytest.raises(ValueError, match="line %d " % line):    # the reference's unpack / int() raise ValueError here too
+        graph.load_edge_text(path)
+    with pytest.raises((ValueError, OverflowError)):            # OverflowError: the 20-digit id, when numpy sees it
+        _reference_text_loop(path)
+
+
+def test_text_loader_missing_file(tmp_path):
+    with pytest.raises(OSError, match="cannot open"):
+        graph.load_edge_text(str(tmp_path / "nope.txt"))
 
 
 def test_splitmix64_matches_the_published_algorithm():

@@ -57,6 +57,50 @@ def test_communities_become_contiguous():
         assert inside >= 9 * 10 - 2          # a block of 10 new ids is (almost exactly) one clique
 
 
+def test_windows_are_deterministic_for_any_thread_count():
+    """The parallel aggregation evaluates a WINDOW of vertices against one state and applies their merges in list order:
+    the permutation is a function of the window length only.  Same graph, 1 / 3 / all host threads, in fresh processes."""
+    import subprocess
+    code = ("import sys, hashlib, numpy as np, torch; sys.path.insert(0, %r); "
+            "from gnnadvisor_osdi21_b200 import reorder as R; "
+            "rng = np.random.default_rng(3); n = 20000; "
+            "c = rng.integers(0, n // 50, 12 * n); "
+            "s = c * 50 + rng.integers(0, 50, 12 * n); d = np.where(rng.random(12 * n) < 0.8, c * 50 + rng.integers(0, 50, 12 * n), rng.integers(0, n, 12 * n)); "
+            "sh = rng.permutation(n); e = torch.from_numpy(np.stack([sh[s], sh[d]]).astype(np.int32)); "
+            "print(' '.join(hashlib.sha1(R.permutation(e, n, window=w).numpy().tobytes()).hexdigest() for w in (0, 1, 64, 1000)))"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for threads in ("1", "3", ""):
+        env = dict(os.environ, OMP_WAIT_POLICY="passive")
+        env.pop("OMP_NUM_THREADS", None)
+        if threads:
+            env["OMP_NUM_THREADS"] = threads
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True, text=True).stdout.split())
+    assert outs[0] == outs[1] == outs[2] and len(outs[0]) == 4
+    assert len(set(outs[0])) >= 3                               # different windows are different (but equally fixed) orders
+
+
+@pytest.mark.parametrize("window", [1, 7, 64, 0])
+def test_every_window_recovers_hidden_communities(window):
+    """200 communities of 50 vertices, 80 % of the edges inside, ids shuffled: whatever the window, the new ids put a
+    community's members next to each other (window 1 is the sequential algorithm)."""
+    rng = np.random.default_rng(8)
+    n, size = 10000, 50
+    m = 10 * n
+    c = rng.integers(0, n // size, m)
+    s = c * size + rng.integers(0, size, m)
+    d = np.where(rng.random(m) < 0.8, c * size + rng.integers(0, size, m), rng.integers(0, n, m))
+    shuffle = rng.permutation(n)
+    e = torch.from_numpy(np.stack([shuffle[s], shuffle[d]]).astype(np.int32))
+    perm = R.permutation(e, n, window=window)
+    assert sorted(perm.tolist()) == list(range(n))
+    out = perm[e.long()]
+    assert _span(out) < 0.35 * _span(e)                         # 20 % of the edges are random: their span cannot shrink
+    new_of_old = perm.numpy()[shuffle]                          # new id of planted vertex i
+    spread = np.array([np.ptp(new_of_old[k * size:(k + 1) * size]) for k in range(n // size)])
+    assert np.median(spread) < 4 * size                         # a community occupies a short id range
+
+
 def test_degenerate_inputs():
     assert R.permutation(torch.zeros(2, 0, dtype=torch.int32), 5).tolist() == [0, 1, 2, 3, 4]
     e = torch.tensor([[0, 1, 1, 2, 2], [0, 1, 2, 1, 2]], dtype=torch.int32)      # self loops + duplicates
