@@ -121,6 +121,57 @@ def test_check_input_messages_follow_the_reference():
         ops.backward_gin(x, x, torch.zeros(8, 8), idx, idx, 0.5, idx, idx, 32, 32, 4)
 
 
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """The reference printf()s "CUDA error" and exit(-1)s after a bad launch (kernel.cu:177-181); the C ABI checks its
+    arguments first and returns GNNA_ERR_INVALID with a message.  Validation happens before any CUDA call, so this runs
+    without a GPU (no compute is launched here: every call below fails or is empty)."""
+    lib = _lib.load()
+    INVALID, OK, UNSUPPORTED = -1, 0, -4
+    x = np.zeros((4, 8), np.float32)
+    ix = np.zeros(8, np.int32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731  (host pointers: never dereferenced by the calls below)
+    null = ctypes.c_void_p(0)
+
+    def err():
+        return lib.gnna_last_error().decode()
+
+    # empty problems are a no-op, not an error
+    assert lib.gnna_sag_f32(null, null, null, null, null, null, 0, 8, 0, 32, 32, 4, null) == OK
+    assert lib.gnna_gcn_aggregate_f32(p(x), p(x), p(ix), p(ix), p(x), p(ix), p(ix), 4, 0, 3, 32, 32, 4, null) == OK
+    # negative sizes, null pointers, missing degrees, unknown modes
+    assert lib.gnna_sag_f32(p(x), p(x), p(ix), p(ix), p(ix), p(ix), -1, 8, 3, 32, 32, 4, null) == INVALID and "negative" in err()
+    assert lib.gnna_sag_f32(null, p(x), p(ix), p(ix), p(ix), p(ix), 4, 8, 3, 32, 32, 4, null) == INVALID and "null feature" in err()
+    assert lib.gnna_sag_f32(p(x), p(x), p(ix), null, p(ix), p(ix), 4, 8, 3, 32, 32, 4, null) == INVALID and "null index" in err()
+    assert lib.gnna_gcn_aggregate_f32(p(x), p(x), p(ix), p(ix), null, p(ix), p(ix), 4, 8, 3, 32, 32, 4, null) == INVALID \
+        and "needs degrees" in err()
+    assert lib.gnna_aggregate_bf16(7, p(x), p(x), p(ix), p(ix), null, 0.0, p(ix), p(ix), 4, 8, 3, 32, 32, 4, null) == INVALID \
+        and "bad mode 7" in err()
+    assert lib.gnna_aggregate_f32_ex(1, p(x), 2, p(x), 4, p(ix), p(ix), p(x), 0.0, p(ix), p(ix), 8, 3, 32, 32, 4, null) == INVALID \
+        and "fewer source rows" in err()
+    assert lib.gnna_aggregate_part_f32_ex(1, 0, p(x), 4, p(x), 4, p(ix), p(ix), p(x), 0.0, p(ix), p(ix), 8, 3, 32, 32, 4, null) == INVALID \
+        and "mode 1 not supported" in err()
+    assert lib.gnna_aggregate_part_f32_ex(0, 0, p(x), 4, p(x), 4, p(ix), p(ix), p(x), 0.0, p(ix), p(ix), 6, 3, 32, 32, 4, null) == INVALID \
+        and "dim % 4" in err()
+    # the fused tile: modes, widths and output range it does not have
+    fused = lib.gnna_aggregate_gemm_fused_bf16
+    assert fused(1, p(x), 0, p(x), 0.0, p(x), null, p(ix), p(ix), p(x), p(ix), p(ix), 4, 64, 16, 3, 32, 32, 4, null) == INVALID \
+        and "mode 1 not supported" in err()
+    assert fused(0, p(x), 0, p(x), 0.0, p(x), null, p(ix), p(ix), null, p(ix), p(ix), 4, 64, 300, 3, 32, 32, 4, null) == INVALID \
+        and "dout 300" in err()
+    assert fused(0, p(x), 0, p(x), 0.0, p(x), null, p(ix), p(ix), null, p(ix), p(ix), 4, 48, 16, 3, 32, 32, 4, null) == UNSUPPORTED \
+        and "no fused tile" in err()
+    # host entry points
+    assert lib.gnna_count_parts_host(0, p(ix), 4) < 0
+    assert lib.gnna_rabbit_reorder_host(p(ix), p(ix), 2, -1, p(ix)) == INVALID
+    bad_edges = np.array([0, 9], np.int32)
+    assert lib.gnna_rabbit_reorder_host(p(bad_edges), p(bad_edges), 2, 4, p(ix)) == INVALID and "out of range at edge 1" in err()
+    n64 = ctypes.c_int64(0)
+    assert lib.gnna_csr_from_edges_host(null, null, 3, 4, p(ix), p(ix), ctypes.byref(n64)) == INVALID and "null pointer" in err()
+    assert lib.gnna_edge_text_scan(b"/nonexistent/edges.txt", ctypes.byref(n64)) == INVALID and "cannot open" in err()
+    info = _lib.LaunchInfo()
+    assert lib.gnna_query_launch(3, 64, 100, 32, 4, ctypes.byref(info)) != OK      # element size 3
+
+
 def test_launch_geometry_follows_the_three_knobs():
     """dimWorker = lanes per neighbour row (pow2, capped by the row), warpPerBlock = warps per CTA."""
     q = ops.launch_info(64, 1000, 32, 8)
