@@ -336,7 +336,64 @@ def run_reference_arm(args):
                              "seconds": sec, "groups_sampled": P, "steps_run": steps},
             "e2e": {"value": v, "unit": "edge*dim/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_extras:
+        try:       # the other half of BASELINE.json's metric ("+ GCN epoch ms") on the same host cores
+            line["extras"] = {"gcn_epoch_ms": cpu_gcn_epoch_ms(oracle, gr, cin, ppn, pnn, degn, threads)}
+        except Exception as e:   # noqa: BLE001
+            line["extras"] = {"gcn_epoch_ms": {"error": str(e)[:200]}}
     print(json.dumps(line))
+
+
+def cpu_gcn_loss_and_grads(oracle, x, y, w, cin, ppn, pnn, degn, threads):
+    """Loss of the 2-layer GCN and the gradients of its two weight matrices (written to w[i].grad), the way the
+    reference's layers compute them: forward T = X*W, out = Ahat*T (kernel.cu:280-310); backward G = Ahat*d_out,
+    d_X = G*W^T, d_W = X^T*G (:436-473; F4: the same CSR both ways).  Aggregations by the oracle, products by torch.mm."""
+    n = x.shape[0]
+
+    def agg(t):
+        return torch.from_numpy(oracle.aggregate(1, t.contiguous().numpy(), cin, degn, 1.0, ppn, pnn, threads=threads))
+    with torch.no_grad():
+        h1 = agg(x @ w[0])
+        a1 = torch.relu(h1)
+        out = agg(a1 @ w[1])
+        logp = torch.log_softmax(out, dim=1)
+        d_out = torch.exp(logp)
+        d_out[torch.arange(n), y] -= 1.0
+        d_out /= n                                     # gradient of nll_loss(log_softmax(out), y), mean reduction
+        g2 = agg(d_out)
+        d_a1, w[1].grad = g2 @ w[1].t(), a1.t() @ g2
+        g1 = agg(d_a1 * (h1 > 0))
+        _unused_d_x, w[0].grad = g1 @ w[0].t(), x.t() @ g1      # the reference computes d_input of layer 1 too (:472)
+    return float(-logp[torch.arange(n), y].mean())
+
+
+def cpu_gcn_epoch_ms(oracle, gr, cin, ppn, pnn, degn, threads, budget_s=40.0):
+    """GCN in-hidden-classes, forward + backward + Adam, as the reference's layers compute it (gnn_conv.py:31-78 on
+    kernel.cu:267-322, :422-476; model and loss GNNA_main.py:142-187) on the host: the aggregations are the oracle's
+    OpenMP port, the dense products torch.mm on the same threads (SURVEY.md 8d R-CPU).  Like the reference, the
+    backward of the first layer computes d_input although nothing uses it (kernel.cu:472)."""
+    n, din, hid, cls = gr["num_nodes"], gr["in_dim"], gr["hidden"], gr["classes"]
+    g = torch.Generator().manual_seed(20212)
+    x = torch.randn(n, din, generator=g)
+    y = torch.ones(n, dtype=torch.long)
+    w = [torch.nn.Parameter((torch.rand(a, b, generator=g) * 2 - 1) / b ** 0.5) for a, b in ((din, hid), (hid, cls))]   # gnn_conv.py:86-88
+    opt = torch.optim.Adam(w, lr=0.01)
+
+    def epoch():
+        loss = cpu_gcn_loss_and_grads(oracle, x, y, w, cin, ppn, pnn, degn, threads)
+        opt.step()
+        return loss
+    t = time.perf_counter()
+    epoch()
+    one = time.perf_counter() - t
+    k = max(1, min(5, int(budget_s / max(one, 1e-6)) - 1))
+    t = time.perf_counter()
+    for _ in range(k):
+        loss = epoch()
+    ms = (time.perf_counter() - t) / k * 1e3
+    return {"ms": ms, "epochs_timed": k, "threads": threads, "final_loss": loss,
+            "model": "GCN %d-%d-%d, fwd+bwd+Adam (GNNA_main.py:142-202) on the host: aggregations = CPU port of the reference "
+                     "kernels (OpenMP), dense products = torch.mm; 1 warm-up epoch" % (din, hid, cls)}
 
 
 def _cpu_workload(args):

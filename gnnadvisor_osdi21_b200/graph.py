@@ -9,6 +9,7 @@ sqrt(max(deg, 1)) in float32.
 """
 import math
 import os
+import time
 
 import numpy as np
 import torch
@@ -260,14 +261,19 @@ class GraphDataset(torch.nn.Module):
     Sources: an edge list (src, dst, num_nodes), a reference-format .npz (src_li, dst_li, num_nodes;
     dataset.py:87-91), a whitespace `src dst` text file (:64-70), or a ready CSR."""
 
-    def __init__(self, dim, num_class, edges=None, path=None, csr=None, device="cuda", verbose=False, seed=20212):
+    def __init__(self, dim, num_class, edges=None, path=None, csr=None, device="cuda", verbose=False, seed=20212, text=None):
         super().__init__()
         self.num_features, self.num_classes = int(dim), int(num_class)
         self.verbose_flag = verbose
         self.reorder_flag = False
         self.device = torch.device(device)
         if path is not None:
-            edges = load_edge_file(path)
+            start = time.perf_counter()
+            edges = load_edge_file(path, text=text)
+            if verbose:                                        # the reference's phase timers (dataset.py:74-79, 91-93)
+                is_npz = text is False or (text is None and str(path).endswith(".npz"))
+                print("# Loading (npz)(s): {:.3f}".format(time.perf_counter() - start) if is_npz
+                      else "# Loading (txt) {:.3f}s ".format(time.perf_counter() - start))
         if edges is not None:
             src, dst, n = edges
             src, dst = np.asarray(src), np.asarray(dst)
@@ -276,7 +282,14 @@ class GraphDataset(torch.nn.Module):
             self.edge_index = np.stack([src, dst])
             self.avg_degree = self.num_edges / self.num_nodes
             self.avg_edgeSpan = float(np.mean(np.abs(src.astype(np.int64) - dst.astype(np.int64)))) if len(src) else 0.0
+            if verbose:                                        # dataset.py:99-102
+                print('# nodes: {}'.format(self.num_nodes))
+                print("# avg_degree: {:.2f}".format(self.avg_degree))
+                print("# avg_edgeSpan: {}".format(int(self.avg_edgeSpan)))
+            start = time.perf_counter()
             rp, ci = csr_from_edges(torch.from_numpy(src), torch.from_numpy(dst), self.num_nodes)
+            if verbose:
+                print("# Build CSR after reordering (s): {:.3f}".format(time.perf_counter() - start))   # :113 (its wording)
         elif csr is not None:
             rp, ci = csr[0].cpu(), csr[1].cpu()
             self.num_nodes = rp.numel() - 1
@@ -299,13 +312,23 @@ class GraphDataset(torch.nn.Module):
     def rabbit_reorder(self):
         """Renumber the vertices for locality and rebuild the CSR and the degree vector (dataset.py:138-175)."""
         if not self.reorder_flag:
+            if self.verbose_flag:
+                print("Reorder flag is not set. Skipped...")
             return
         from . import reorder as _reorder
+        if self.verbose_flag:
+            print("Reorder flag is set. Continue...")
+        start = time.perf_counter()
         new_edges = _reorder.reorder(torch.as_tensor(self.edge_index).to(torch.int32))
+        if self.verbose_flag:
+            print("# Reorder time (s): {}".format(time.perf_counter() - start))
         self.edge_index = new_edges.numpy()
+        start = time.perf_counter()
         rp, ci = csr_from_edges(new_edges[0], new_edges[1], self.num_nodes)
         self.row_pointers, self.column_index = rp, ci
         self._refresh_degrees()
+        if self.verbose_flag:
+            print("# Re-Build CSR (s): {:.3f}".format(time.perf_counter() - start))
 
 
 class custom_dataset(GraphDataset):
@@ -315,7 +338,7 @@ class custom_dataset(GraphDataset):
     def __init__(self, path, dim, num_class, load_from_txt=True, verbose=False, device="cuda"):
         if not load_from_txt and not str(path).endswith(".npz"):
             raise ValueError("graph file must be a .npz file")          # dataset.py:83-84
-        super().__init__(dim, num_class, edges=load_edge_file(path, text=bool(load_from_txt)), device=device, verbose=verbose)
+        super().__init__(dim, num_class, path=path, text=bool(load_from_txt), device=device, verbose=verbose)
         self.load_from_txt = load_from_txt
         n = self.num_nodes
         idx = torch.arange(n, device=self.device)

@@ -86,6 +86,29 @@ def test_custom_dataset_has_the_reference_constructor(tmp_path):
         graph.custom_dataset(txt, 16, 10, load_from_txt=False, device="cpu")
 
 
+def test_verbose_dataset_prints_the_reference_phase_lines(tmp_path, capsys):
+    """dataset.py's verbose phase timers (:77-79, :91-93, :99-102, :113, :152-175), which the reference's log scrapers read."""
+    rng = np.random.default_rng(6)
+    src, dst = rng.integers(0, 60, 500), rng.integers(0, 60, 500)
+    txt = str(tmp_path / "g.txt")
+    with open(txt, "w") as f:
+        f.write("".join("%d %d\n" % (a, b) for a, b in zip(src, dst)))
+    ds = graph.custom_dataset(txt, 8, 3, load_from_txt=True, verbose=True, device="cpu")
+    ds.rabbit_reorder()                                       # flag not set
+    ds.reorder_flag = True
+    before = ds.column_index.clone()
+    ds.rabbit_reorder()
+    out = capsys.readouterr().out
+    for needle in ("# Loading (txt) ", "# nodes: %d" % ds.num_nodes, "# avg_degree: ", "# avg_edgeSpan: ", "# Build CSR after reordering (s): ",
+                   "Reorder flag is not set. Skipped...", "Reorder flag is set. Continue...", "# Reorder time (s): ", "# Re-Build CSR (s): "):
+        assert needle in out, needle
+    assert ds.column_index.numel() == before.numel() and int(ds.row_pointers[-1]) == before.numel()
+    npz = str(tmp_path / "g.npz")
+    graph.save_npz(npz, src, dst, 60)
+    graph.custom_dataset(npz, 8, 3, load_from_txt=False, verbose=True, device="cpu")
+    assert "# Loading (npz)(s): " in capsys.readouterr().out
+
+
 def _reference_text_loop(path):
     """dataset.py:62-72 as written: the per-line loop of the reference."""
     src_li, dst_li, nodes = [], [], set()
