@@ -35,6 +35,21 @@ def in_block_fraction(perm, s, d, block=512):
     return float(np.mean(perm[s] // block == perm[d] // block))
 
 
+def halo_rows(perm, s, d, n, world=8):
+    """Rows a rank must receive per aggregation when the relabelled graph is cut into `world` edge-balanced vertex ranges
+    (dist.partition_ranges with row weight 0): (mean, max) over the ranks of the number of distinct remote neighbours."""
+    ps, pd = perm[np.concatenate([s, d])], perm[np.concatenate([d, s])]          # symmetric
+    deg = np.bincount(ps, minlength=n)
+    cum = np.concatenate([[0], np.cumsum(deg)])
+    cuts = np.searchsorted(cum, [cum[-1] * g // world for g in range(world + 1)])
+    cuts[0], cuts[-1] = 0, n
+    owner = np.searchsorted(cuts, ps, side="right") - 1
+    remote = (pd < cuts[owner]) | (pd >= cuts[owner + 1])
+    key = np.unique(owner[remote].astype(np.int64) * n + pd[remote])
+    per_rank = np.bincount(key // n, minlength=world)
+    return float(per_rank.mean()), int(per_rank.max())
+
+
 def main():
     args = [int(a) for a in sys.argv[1:]]
     n = args[0] if args else 600000
@@ -44,15 +59,16 @@ def main():
                          ("R-MAT look-alike", tuple(t.numpy() for t in graph.stream_pairs(n, 0, 12 * n, kind="rmat", seed=3)))):
         e = torch.from_numpy(np.stack([s, d]).astype(np.int32))
         ident = np.arange(n)
-        print("\n%s: %d vertices, %d edge pairs, %d host threads; as given: avg edge span %.0f, same-block share %.3f"
-              % (name, n, len(s), threads, span(ident, s, d), in_block_fraction(ident, s, d)), flush=True)
+        print("\n%s: %d vertices, %d edge pairs, %d host threads; as given: avg edge span %.0f, same-block share %.3f, "
+              "halo rows per rank at 8 ranks mean %.0f / max %d"
+              % ((name, n, len(s), threads, span(ident, s, d), in_block_fraction(ident, s, d)) + halo_rows(ident, s, d, n)), flush=True)
         for w in windows:
             t = time.perf_counter()
             perm = reorder.permutation(e, n, window=w).numpy().astype(np.int64)
             dt = time.perf_counter() - t
             assert np.array_equal(np.sort(perm), ident)
-            print("  window %6d: %7.2f s   avg edge span %9.0f   same-block share %.3f"
-                  % (w, dt, span(perm, s, d), in_block_fraction(perm, s, d)), flush=True)
+            print("  window %6d: %7.2f s   avg edge span %9.0f   same-block share %.3f   halo rows per rank at 8 ranks mean %.0f / max %d"
+                  % ((w, dt, span(perm, s, d), in_block_fraction(perm, s, d)) + halo_rows(perm, s, d, n)), flush=True)
 
 
 if __name__ == "__main__":
