@@ -1,0 +1,72 @@
+"""Property-based (hypothesis) checks of the integer host code of the path against its references: the group table
+against the oracle's restatement of GNNAdvisor.cpp:210-251, the CSR builder against scipy's coo -> csr
+(dataset.py:108-111), the text loader against the reference's per-line loop (dataset.py:62-72).  Bit-exact, CPU only."""
+import numpy as np
+import scipy.sparse as sp
+import torch
+from hypothesis import given, settings, strategies as st
+
+import oracle
+from gnnadvisor_osdi21_b200 import graph, ops
+
+degree_lists = st.lists(st.one_of(st.just(0), st.integers(0, 9), st.integers(10, 300)), min_size=1, max_size=60)
+
+
+@settings(max_examples=60, deadline=None)
+@given(degs=degree_lists, ps=st.sampled_from([1, 2, 3, 7, 32, 64, 512]))
+def test_build_part_host_equals_the_oracle_for_any_degree_sequence(degs, ps):
+    rp = np.concatenate([[0], np.cumsum(degs)]).astype(np.int32)
+    t = torch.from_numpy(rp)
+    # exact table (what this runtime consumes): terminal always indptr[-1]
+    pp, pn = ops.build_part_exact(ps, t)
+    opp, opn = oracle.build_part(ps, rp, exact=True)
+    assert np.array_equal(pp.numpy(), opp) and np.array_equal(pn.numpy(), opn)
+    assert len(pn) == sum(-(-d // ps) for d in degs) and int(pp[-1]) == int(rp[-1])
+    assert all(0 < int(pp[i + 1]) - int(pp[i]) <= ps for i in range(len(pn)))        # every group has 1..ps neighbours
+    # compat table: the reference's float32 tensors bit for bit, F6 (terminal 0 after an isolated last node) included
+    cpp, cpn = ops.build_part(ps, t, compat=True)
+    fpp, fpn = oracle.build_part_f32(ps, rp)
+    assert cpp.dtype == torch.float32 and np.array_equal(cpp.numpy(), fpp) and np.array_equal(cpn.numpy(), fpn)
+    if degs[-1] == 0 and len(pn):
+        assert float(cpp[-1]) == 0.0
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st.integers(1, 40), pairs=st.lists(st.tuples(st.integers(0, 39), st.integers(0, 39)), max_size=200),
+       dup=st.integers(1, 3))
+def test_native_csr_equals_scipy_for_any_edge_list(n, pairs, dup):
+    pairs = [(a % n, b % n) for a, b in pairs] * dup
+    src = np.array([p[0] for p in pairs], dtype=np.int64)
+    dst = np.array([p[1] for p in pairs], dtype=np.int64)
+    rp, ci = graph.csr_from_edges(src, dst, n, native=True)
+    csr = sp.coo_matrix((np.ones(len(src)), (src, dst)), shape=(n, n)).tocsr()
+    csr.sort_indices()
+    assert np.array_equal(rp.numpy(), csr.indptr) and np.array_equal(ci.numpy(), csr.indices)
+    rp2, ci2 = graph.csr_from_edges(src, dst, n, native=False)
+    assert torch.equal(rp, rp2) and torch.equal(ci, ci2)
+
+
+blank = st.sampled_from([" ", "\t", "  ", " \t "])
+
+
+@settings(max_examples=40, deadline=None)
+@given(edges=st.lists(st.tuples(st.integers(0, 10 ** 9), st.integers(0, 10 ** 9), blank, st.sampled_from(["", " ", "\t"]),
+                                st.sampled_from(["", " "])), max_size=50),
+       crlf=st.booleans(), final_newline=st.booleans())
+def test_text_loader_equals_the_reference_loop_for_any_spacing(tmp_path_factory, edges, crlf, final_newline):
+    text = ("\r\n" if crlf else "\n").join("%s%d%s%d%s" % (lead, a, sep, b, trail) for a, b, sep, trail, lead in edges)
+    if final_newline and edges:
+        text += "\r\n" if crlf else "\n"
+    path = str(tmp_path_factory.mktemp("txt") / "g.txt")
+    with open(path, "w", newline="") as f:
+        f.write(text)
+    s, d, n = graph.load_edge_text(path)
+    # dataset.py:62-72 (split() takes the same blanks, '\r' included)
+    rs, rd = [], []
+    with open(path, newline="") as fp:
+        for line in fp:
+            a, b = line.strip("\n").split()
+            rs.append(int(a))
+            rd.append(int(b))
+    assert s.tolist() == rs and d.tolist() == rd
+    assert n == (max(rs + rd) + 1 if rs else 0)
