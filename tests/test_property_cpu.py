@@ -70,3 +70,16 @@ def test_text_loader_equals_the_reference_loop_for_any_spacing(tmp_path_factory,
             rd.append(int(b))
     assert s.tolist() == rs and d.tolist() == rd
     assert n == (max(rs + rd) + 1 if rs else 0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st.integers(1, 50), pairs=st.lists(st.tuples(st.integers(0, 49), st.integers(0, 49)), max_size=300),
+       window=st.sampled_from([0, 1, 2, 5, 1000]))
+def test_reorder_is_a_permutation_for_any_edge_list_and_window(n, pairs, window):
+    """rabbit.reorder's contract (reorder.cpp:235-290): every vertex gets exactly one new id, isolated ones included, whatever
+    the edge list holds (self loops, duplicates, one direction only); and the same call gives the same answer."""
+    from gnnadvisor_osdi21_b200 import reorder
+    e = torch.tensor([[a % n for a, _ in pairs], [b % n for _, b in pairs]], dtype=torch.int32).reshape(2, -1)
+    perm = reorder.permutation(e, n, window=window)
+    assert sorted(perm.tolist()) == list(range(n))
+    assert torch.equal(perm, reorder.permutation(e, n, window=window))
