@@ -184,8 +184,8 @@ extern "C" int gnna_edge_text_parse(const char *path_host, int64_t *src_host, in
 }
 
 // COO -> CSR with duplicates merged and columns ascending.  Row ranges of equal width are the buckets of a two-level
-// counting sort: (1) every thread histograms its slice of the edge list over the buckets, (2) a prefix sum over
-// (bucket, thread) gives each thread a private range inside each bucket, so the scatter needs no atomics and is
+// counting sort: (1) the edge list is cut into slices, each histogrammed over the buckets, (2) a prefix sum over
+// (bucket, slice) gives each slice a private range inside each bucket, so the scatter needs no atomics and is
 // deterministic, (3) buckets are sorted as packed (row << 32 | col) keys and made unique independently -- a bucket is a few
 // 10^4 keys, cache-resident -- and (4) the unique keys are copied to their final offsets.
 extern "C" int gnna_csr_from_edges_host(const int64_t *src_host, const int64_t *dst_host, int64_t num_edges,
@@ -209,13 +209,14 @@ extern "C" int gnna_csr_from_edges_host(const int64_t *src_host, const int64_t *
         while (((N - 1) >> shift) + 1 > want_buckets) shift++;
     }
     const int64_t B = ((N - 1) >> shift) + 1;
-    // every region below runs on the same team: libgomp re-docks its pool (a spin-wait of ~100 ms) whenever the team size changes
+    // The edge list is cut into T slices, one histogram each.  T is a number of SLICES, not a promise about the team: the
+    // loops below hand slices to whatever threads the runtime grants (all regions ask for the same team size: libgomp
+    // re-docks its pool, a spin-wait of ~100 ms in a sandboxed container, whenever the size changes).
     const int T = std::max(1, omp_get_max_threads());
     std::vector<int64_t> hist((size_t)T * B, 0);
     long long bad = -1;
-#pragma omp parallel num_threads(T)
-    {
-        const int t = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
         const int64_t e0 = E * t / T, e1 = E * (t + 1) / T;
         int64_t *h = hist.data() + (size_t)t * B;
         long long my_bad = -1;
@@ -246,9 +247,8 @@ extern "C" int gnna_csr_from_edges_host(const int64_t *src_host, const int64_t *
     }
     std::unique_ptr<uint64_t[]> keys_mem(new uint64_t[(size_t)E]);   // not value-initialised: first touched by the scatter's threads
     uint64_t *const keys = keys_mem.get();
-#pragma omp parallel num_threads(T)
-    {
-        const int t = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
         const int64_t e0 = E * t / T, e1 = E * (t + 1) / T;
         int64_t *cur = hist.data() + (size_t)t * B;
         for (int64_t i = e0; i < e1; i++) {
