@@ -83,3 +83,43 @@ def test_reorder_is_a_permutation_for_any_edge_list_and_window(n, pairs, window)
     perm = reorder.permutation(e, n, window=window)
     assert sorted(perm.tolist()) == list(range(n))
     assert torch.equal(perm, reorder.permutation(e, n, window=window))
+
+
+_REF = None
+
+
+def _reference():
+    """The reference's own extension, compiled from /root/reference by oracle/build_ref.py (oracle/_ref/, git-ignored).
+    build_part is host code, so it runs without a GPU."""
+    global _REF
+    if _REF is None:
+        import build_ref
+        _REF = build_ref.load_ref() or False
+    return _REF
+
+
+@settings(max_examples=80, deadline=None, derandomize=True)
+@given(degs=degree_lists, ps=st.sampled_from([1, 2, 3, 7, 32, 64, 512]))
+def test_build_part_equals_the_reference_itself_run_live(degs, ps):
+    """Not a golden file: the reference's build_part (GNNAdvisor.cpp:210-251) executed here on the same indptr.  The
+    compat table of the product and the oracle's float table must be its two float32 tensors bit for bit (F5 rounding,
+    F6 terminal); the exact table must equal it after the caller's `.int()` (GNNA_main.py:109-110) whenever the last node
+    has a neighbour."""
+    ref = _reference()
+    if not ref:
+        import pytest
+        pytest.skip("oracle/_ref/GNNAdvisor_ref.so not built (needs /root/reference)")
+    rp = np.concatenate([[0], np.cumsum(degs)]).astype(np.int32)
+    t = torch.from_numpy(rp)
+    rpp, rpn = ref.build_part(ps, t)
+    assert rpp.dtype == torch.float32 and rpn.dtype == torch.float32
+    cpp, cpn = ops.build_part(ps, t, compat=True)
+    assert torch.equal(cpp, rpp) and torch.equal(cpn, rpn)
+    fpp, fpn = oracle.build_part_f32(ps, rp)
+    assert np.array_equal(fpp, rpp.numpy()) and np.array_equal(fpn, rpn.numpy())
+    epp, epn = ops.build_part_exact(ps, t)
+    assert torch.equal(epn, rpn.int())
+    if degs[-1] > 0:
+        assert torch.equal(epp, rpp.int())
+    else:                                                       # F6: the reference leaves the terminal 0
+        assert torch.equal(epp[:-1], rpp.int()[:-1]) and int(epp[-1]) == int(rp[-1])
