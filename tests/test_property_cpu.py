@@ -123,3 +123,40 @@ def test_build_part_equals_the_reference_itself_run_live(degs, ps):
         assert torch.equal(epp, rpp.int())
     else:                                                       # F6: the reference leaves the terminal 0
         assert torch.equal(epp[:-1], rpp.int()[:-1]) and int(epp[-1]) == int(rp[-1])
+
+
+class _Dataset:
+    def __init__(self, n, e, feat, span):
+        self.num_nodes, self.num_features = n, feat
+        self.avg_degree, self.avg_edgeSpan = e / n, span
+        self.reorder_flag, self.row_pointers, self.column_index, self.reordered = None, None, None, 0
+
+    def rabbit_reorder(self):
+        self.reordered += 1
+
+
+@settings(max_examples=200, deadline=None, derandomize=True)
+@given(n=st.integers(2, 3_000_000), avg=st.floats(1.0, 600.0), feat=st.integers(1, 4000), hid=st.integers(1, 2048),
+       smem=st.sampled_from([16, 48, 64, 100, 164, 227]), span=st.floats(0.0, 1e6), rabbit=st.booleans(), manual=st.booleans())
+def test_decider_equals_the_reference_decider_run_live(n, avg, feat, hid, smem, span, rabbit, manual):
+    """param.py:52-120 of the reference, imported here, against param.InputProperty on the same dataset statistics: partSize,
+    the per-layer dimWorker / warpPerBlock, the reorder decision and how often the dataset is asked to reorder."""
+    import importlib.util
+    import os
+    import pytest
+    from gnnadvisor_osdi21_b200 import param
+    path = "/root/reference/GNNAdvisor/param.py"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is only mounted in the authoring container")
+    spec = importlib.util.spec_from_file_location("ref_param_live", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    out = []
+    for cls in (param.InputProperty, ref.inputProperty):
+        ds = _Dataset(n, int(avg * n), feat, span)
+        p = cls(None, None, None, 32, 32, 4, smem, hiddenDim=hid, dataset_obj=ds, enable_rabbit=rabbit, manual_mode=manual)
+        p.decider()
+        a = (p.set_input().dimWorker, p.warpPerBlock)
+        b = (p.set_hidden().dimWorker, p.warpPerBlock)
+        out.append((p.partSize, a, b, bool(p.reorder_status), ds.reorder_flag, ds.reordered))
+    assert out[0] == out[1]
