@@ -30,6 +30,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
+#include <memory>
 #include <numeric>
 #include <utility>
 #include <vector>
@@ -139,26 +140,66 @@ extern "C" int gnna_rabbit_reorder_host_ex(const int32_t *src, const int32_t *ds
     }
     if (window <= 0) window = std::min<int64_t>(16384, std::max<int64_t>(1, num_nodes / 64));
 
-    // 1. symmetric weighted adjacency, no self loops, duplicates merged
-    // (the edge list passes are the bulk of the time at 10^8 edges: all host threads, as the reference's OpenMP build)
-    std::vector<uint64_t> keys((size_t)num_edges * 2);
+    // 1. symmetric weighted adjacency, no self loops, duplicates merged.  Both directions of every edge become a packed
+    // key (a << 32 | b); the keys are brought into order by a two-level counting sort like csrc/dataset.cu's: slices of the
+    // edge list are histogrammed over row-range buckets, a prefix sum over (bucket, slice) gives every slice private slots
+    // (no atomics, deterministic), and the buckets -- ~16 K keys, cache-resident -- are sorted independently; buckets are
+    // ascending row ranges, so the array is then sorted as a whole.
+    int shift = 0;
+    {
+        const int64_t want_buckets = std::max<int64_t>(1, std::min<int64_t>(num_edges / 8192 + 1, 1 << 16));
+        while ((((int64_t)n - 1) >> shift) + 1 > want_buckets) shift++;
+    }
+    const int64_t B = (((int64_t)n - 1) >> shift) + 1;
+    const int T = std::max(1, omp_get_max_threads());          // slices (handed to whatever team the runtime grants)
+    std::vector<int64_t> hist((size_t)T * B, 0);
     long long bad = -1;
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < num_edges; i++) {
-        const int32_t a = src[i], b = dst[i];
-        if (a < 0 || a >= n || b < 0 || b >= n) {
-#pragma omp critical
-            if (bad < 0 || i < bad) bad = i;
-            keys[2 * i] = keys[2 * i + 1] = ~0ull;
-            continue;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
+        int64_t *h = hist.data() + (size_t)t * B;
+        long long my_bad = -1;
+        for (int64_t i = num_edges * t / T; i < num_edges * (t + 1) / T; i++) {
+            const int32_t a = src[i], b = dst[i];
+            if (a < 0 || a >= n || b < 0 || b >= n) { if (my_bad < 0) my_bad = i; continue; }
+            if (a == b) continue;                              // self loop: dropped
+            h[a >> shift]++;
+            h[b >> shift]++;
         }
-        if (a == b) { keys[2 * i] = keys[2 * i + 1] = ~0ull; continue; }     // self loop: dropped below
-        keys[2 * i] = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
-        keys[2 * i + 1] = ((uint64_t)(uint32_t)b << 32) | (uint32_t)a;
+        if (my_bad >= 0) {
+#pragma omp critical
+            if (bad < 0 || my_bad < bad) bad = my_bad;
+        }
     }
     GNNA_REQUIRE(bad < 0, "rabbit_reorder: vertex id out of range at edge %lld", bad);
-    __gnu_parallel::sort(keys.begin(), keys.end());
-    const size_t nkeys = (size_t)(std::lower_bound(keys.begin(), keys.end(), ~0ull) - keys.begin());
+    std::vector<int64_t> bucket_begin((size_t)B + 1, 0);
+    {
+        int64_t run = 0;
+        for (int64_t b = 0; b < B; b++) {
+            bucket_begin[b] = run;
+            for (int t = 0; t < T; t++) {
+                const int64_t c = hist[(size_t)t * B + b];
+                hist[(size_t)t * B + b] = run;                 // becomes slice t's write cursor in bucket b
+                run += c;
+            }
+        }
+        bucket_begin[B] = run;
+    }
+    const size_t nkeys = (size_t)bucket_begin[B];
+    std::unique_ptr<uint64_t[]> keys_mem(new uint64_t[nkeys ? nkeys : 1]);   // first touched by the scatter's threads
+    uint64_t *const keys = keys_mem.get();
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
+        int64_t *cur = hist.data() + (size_t)t * B;
+        for (int64_t i = num_edges * t / T; i < num_edges * (t + 1) / T; i++) {
+            const int32_t a = src[i], b = dst[i];
+            if (a == b) continue;
+            keys[cur[a >> shift]++] = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
+            keys[cur[b >> shift]++] = ((uint64_t)(uint32_t)b << 32) | (uint32_t)a;
+        }
+    }
+#pragma omp parallel for schedule(dynamic, 4) num_threads(T)
+    for (int64_t b = 0; b < B; b++) std::sort(keys + bucket_begin[b], keys + bucket_begin[b + 1]);
+    std::vector<int64_t>().swap(hist);
     lap("edge keys + sort");
     Dendrogram g;
     g.es.resize(n);
@@ -196,7 +237,7 @@ extern "C" int gnna_rabbit_reorder_host_ex(const int32_t *src, const int32_t *ds
         tot += s;
     }
     g.tot_wgt = tot;
-    std::vector<uint64_t>().swap(keys);
+    keys_mem.reset();
     std::vector<size_t>().swap(first);
     lap("adjacency");
 
