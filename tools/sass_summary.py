@@ -1,6 +1,6 @@
 """Per-kernel SASS evidence of the shipped libgnna_b200.so (runs without a GPU: cuobjdump + c++filt).
 
-For every kernel of the library: instruction count and how often the mnemonics occur that say what the kernel is built
+For every kernel of the library: registers, stack bytes (spills), static shared memory, instruction count and how often the mnemonics occur that say what the kernel is built
 from (B200_PROFILING.md, "What proves a Blackwell-native kernel"): UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st,
 UTCBAR = tcgen05.commit, UBLKCP / UTMALDG = TMA bulk copies, SYNCS = mbarrier, LDGSTS = cp.async, LDG.E.128 = 128-bit
 gathers, REDG.E.ADD.F32x4 = red.global.add.v4.f32, FHADD.BF16 = mixed-precision bf16 accumulate, HMMA = legacy mma.sync.
@@ -41,24 +41,32 @@ def main():
             continue
         if cur is not None and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
             kernels[cur].append(line)
+    res = {}
+    usage = subprocess.run([CUOBJDUMP, "-res-usage", LIB], capture_output=True, text=True, check=True).stdout.splitlines()
+    for i, line in enumerate(usage):
+        m = re.match(r"\s*Function (\S+):", line)
+        if m and i + 1 < len(usage):
+            f = dict(kv.split(":") for kv in usage[i + 1].split() if ":" in kv and "[" not in kv)
+            res[m.group(1)] = (int(f.get("REG", 0)), int(f.get("STACK", 0)), int(f.get("SHARED", 0)))
     names = list(kernels)
     dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
     print("SASS summary of %s (sm_100a, %d kernels); columns = occurrences per kernel" % (os.path.relpath(LIB, ROOT), len(names)))
-    head = ["instr"] + [p[0] for p in PATTERNS]
+    head = ["regs", "stack B", "static smem", "instr"] + [p[0] for p in PATTERNS]
     print("%-78s %s" % ("kernel", " ".join("%13s" % h for h in head)))
     totals = collections.Counter()
     rows = []
     for mangled, pretty in zip(names, dem):
         body = kernels[mangled]
-        counts = [len(body)] + [sum(1 for ln in body if re.search(rx, ln)) for _, rx in PATTERNS]
+        counts = list(res.get(mangled, (0, 0, 0))) + [len(body)] + [sum(1 for ln in body if re.search(rx, ln)) for _, rx in PATTERNS]
         for h, c in zip(head, counts):
-            totals[h] += c
+            totals[h] = max(totals[h], c) if h in ("regs", "stack B", "static smem") else totals[h] + c
         rows.append((short(pretty), counts))
     for name, counts in sorted(rows):
         print("%-78s %s" % (name[:78], " ".join("%13d" % c for c in counts)))
-    print("%-78s %s" % ("TOTAL", " ".join("%13d" % totals[h] for h in head)))
-    tc = sorted({n.split("<")[0] for n, c in rows if c[1] > 0})
-    tma = sorted({n.split("<")[0] for n, c in rows if c[5] > 0})
+    print("%-78s %s" % ("TOTAL (max for regs / stack / smem)", " ".join("%13d" % totals[h] for h in head)))
+    tc = sorted({n.split("<")[0] for n, c in rows if c[4] > 0})
+    tma = sorted({n.split("<")[0] for n, c in rows if c[8] > 0})
+    print("\nkernels with a stack frame (spills or local arrays): %s" % (", ".join(sorted({n.split('<')[0] for n, c in rows if c[1] > 0})) or "none"))
     print("\nkernels issuing tcgen05.mma: %s" % ", ".join(tc))
     print("kernels using TMA bulk copies: %s" % ", ".join(tma))
     print("kernels with legacy mma.sync (HMMA): %s" % (", ".join(sorted({n.split('<')[0] for n, c in rows if c[-1] > 0})) or "none"))
