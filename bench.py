@@ -337,11 +337,40 @@ def run_reference_arm(args):
             "e2e": {"value": v, "unit": "edge*dim/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if not args.no_extras:
+        line["extras"] = {}
         try:       # the other half of BASELINE.json's metric ("+ GCN epoch ms") on the same host cores
-            line["extras"] = {"gcn_epoch_ms": cpu_gcn_epoch_ms(oracle, gr, cin, ppn, pnn, degn, threads)}
+            line["extras"]["gcn_epoch_ms"] = cpu_gcn_epoch_ms(oracle, gr, cin, ppn, pnn, degn, threads)
         except Exception as e:   # noqa: BLE001
-            line["extras"] = {"gcn_epoch_ms": {"error": str(e)[:200]}}
+            line["extras"]["gcn_epoch_ms"] = {"error": str(e)[:200]}
+        try:       # SURVEY.md 8d's other CPU restatement (a library sparse product): reported next to the port, which stays `value`
+            ts = cpu_torch_sparse(rp, ci, deg, X, E, D, threads)
+            ts["vs_port"] = ts["edge_dim_per_s"] / v
+            line["extras"]["torch_sparse_csr"] = ts
+        except Exception as e:   # noqa: BLE001
+            line["extras"]["torch_sparse_csr"] = {"error": str(e)[:200]}
     print(json.dumps(line))
+
+
+def cpu_torch_sparse(rp, ci, deg, X, E, D, threads, reps=3):
+    """The same GCN aggregation as ONE torch.sparse CSR product on the host threads: A_w @ X with values n_i * n_j
+    (SURVEY.md 8d "R-CPU": what unitest.py's torch_sparse.spmm reference does for plain SAG).  Best of `reps` after one
+    warm-up.  Reported beside the OpenMP port of the reference kernels (the arm's `value`: the reference's ALGORITHM --
+    groups, un-fused roundings -- on the host), so the reader sees how a library product with fused multiply-adds compares:
+    vs_port > 1 means the library is the faster CPU baseline by that factor."""
+    n = rp.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(n), (rp[1:] - rp[:-1]).long())
+    vals = deg[rows] * deg[ci.long()]
+    A = torch.sparse_csr_tensor(rp, ci, vals, size=(n, n))
+    del rows
+    A @ X
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        A @ X
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return {"ms": best * 1e3, "edge_dim_per_s": E * D / best, "threads": threads,
+            "what": "torch.sparse_csr_tensor(values n_i*n_j) @ X, fp32, best of %d" % reps}
 
 
 def cpu_gcn_loss_and_grads(oracle, x, y, w, cin, ppn, pnn, degn, threads):

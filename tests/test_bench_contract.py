@@ -24,6 +24,8 @@ def test_reference_arm_prints_one_json_line_on_cpu():
     assert line["config"]["num_nodes"] == 2708 and "workload" in line["config"] and "model" not in line["config"]
     ep = line["extras"]["gcn_epoch_ms"]                     # the other half of the metric, on the same host cores
     assert ep["ms"] > 0 and ep["epochs_timed"] >= 1 and "1433-16-7" in ep["model"] and ep["final_loss"] == ep["final_loss"]
+    ts = line["extras"]["torch_sparse_csr"]
+    assert ts["ms"] > 0 and ts["vs_port"] > 0
     # the CPU arm must not load the product: the graph is built with torch ops, the arithmetic is the oracle's
     assert "libgnna_b200" not in out.stderr
 
