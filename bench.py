@@ -19,7 +19,8 @@ One JSON line on stdout (rank 0):
   extras       gcn_epoch_ms (2-layer GCN fwd+bwd+Adam), bf16 gather variant, the reference's own CUDA
                kernels recompiled for sm_100a on the same tensors (ref_gpu), clocks.
 --impl reference times the CPU port of the reference algorithm (the reference has no CPU path of its
-own) on all host cores.
+own) on all host cores; its extras carry the GCN epoch on the host (port + torch.mm) and the
+same aggregation as a torch.sparse CSR product, for comparison.
 """
 import argparse
 import json
