@@ -151,12 +151,19 @@ def test_decider_equals_the_reference_decider_run_live(n, avg, feat, hid, smem, 
     spec = importlib.util.spec_from_file_location("ref_param_live", path)
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
+    import contextlib
+    import io
     out = []
     for cls in (param.InputProperty, ref.inputProperty):
         ds = _Dataset(n, int(avg * n), feat, span)
-        p = cls(None, None, None, 32, 32, 4, smem, hiddenDim=hid, dataset_obj=ds, enable_rabbit=rabbit, manual_mode=manual)
-        p.decider()
-        a = (p.set_input().dimWorker, p.warpPerBlock)
-        b = (p.set_hidden().dimWorker, p.warpPerBlock)
-        out.append((p.partSize, a, b, bool(p.reorder_status), ds.reorder_flag, ds.reordered))
+        text = io.StringIO()
+        with contextlib.redirect_stdout(text):               # verbose mode: the lines the reference's log scrapers read
+            p = cls(None, None, None, 32, 32, 4, smem, hiddenDim=hid, dataset_obj=ds, enable_rabbit=rabbit, manual_mode=manual,
+                    verbose=True)
+            p.decider()
+            a = (p.set_input().dimWorker, p.warpPerBlock)
+            p.print_param()
+            b = (p.set_hidden().dimWorker, p.warpPerBlock)
+            p.print_param()
+        out.append((p.partSize, a, b, bool(p.reorder_status), ds.reorder_flag, ds.reordered, text.getvalue()))
     assert out[0] == out[1]
