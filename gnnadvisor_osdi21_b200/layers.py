@@ -197,7 +197,8 @@ class _ConvBase(torch.nn.Module):
             raise ValueError("gather_dtype must be 'fp32' or 'bf16'")
         self.gather_dtype = gather_dtype
         self.fused = bool(fused)
-        self.weights = torch.nn.Parameter(torch.empty(input_dim, output_dim))
+        # randn first, like the reference (gnn_conv.py:83, 131): the same torch seed then gives the same initial weights
+        self.weights = torch.nn.Parameter(torch.randn(input_dim, output_dim))
         self.reset_parameters()
 
     def reset_parameters(self):

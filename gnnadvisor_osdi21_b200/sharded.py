@@ -204,7 +204,7 @@ class ShardedGNNAFunction_GIN(torch.autograd.Function):
 class _ShardedConv(torch.nn.Module):
     def __init__(self, input_dim, output_dim):
         super().__init__()
-        self.weights = torch.nn.Parameter(torch.empty(input_dim, output_dim))
+        self.weights = torch.nn.Parameter(torch.randn(input_dim, output_dim))      # drawn like gnn_conv.py:83 (same seed, same weights)
         bound = 1.0 / math.sqrt(output_dim)                              # gnn_conv.py:86-88, 136-138
         with torch.no_grad():
             self.weights.uniform_(-bound, bound)

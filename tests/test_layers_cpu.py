@@ -195,3 +195,35 @@ def test_layer_switches_route_to_the_right_operators(setup):
     assert layers.fused_tile_supported(256, "bf16") and not layers.fused_tile_supported(256, "fp32")
     with pytest.raises(ValueError):
         layers.GCNConv(4, 4, gather_dtype="fp16")
+
+
+REF_PY = "/root/reference/GNNAdvisor"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_PY), reason="the reference tree is only mounted in the authoring container")
+def test_same_seed_gives_the_reference_layers_initial_weights():
+    """gnn_conv.py:80-88, 128-138 imported unchanged (compat/ provides `GNNAdvisor`): a model built after
+    torch.manual_seed(s) starts from the same weights here and there, layer by layer."""
+    import importlib
+    import os
+    import sys
+    from gnnadvisor_osdi21_b200 import sharded
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnnadvisor_osdi21_b200", "compat")
+    saved = {n: sys.modules.pop(n) for n in ("GNNAdvisor", "gnn_conv") if n in sys.modules}
+    sys.path[:0] = [compat, REF_PY]
+    try:
+        ref = importlib.import_module("gnn_conv")
+        for ours, theirs in ((layers.GCNConv, ref.GCNConv), (layers.GINConv, ref.GINConv),
+                             (sharded.ShardedGCNConv, ref.GCNConv), (sharded.ShardedGINConv, ref.GINConv)):
+            torch.manual_seed(123)
+            a = [ours(7, 5), ours(5, 3)]
+            torch.manual_seed(123)
+            b = [theirs(7, 5), theirs(5, 3)]
+            for x, y in zip(a, b):
+                assert torch.equal(x.weights, y.weights)
+            assert getattr(a[0], "eplison", None) == getattr(b[0], "eplison", None)
+    finally:
+        del sys.path[:2]
+        for n in ("GNNAdvisor", "gnn_conv"):
+            sys.modules.pop(n, None)
+        sys.modules.update(saved)
