@@ -203,3 +203,63 @@ def test_exact_lookalike_sizes_and_last_node():
     assert int(rp[-1]) == 10556 and int(rp[-1] - rp[-2]) > 0
     rp2, ci2 = graph.synth_graph(2708, 10556, kind="uniform", seed=20211)
     assert torch.equal(rp, rp2) and torch.equal(ci, ci2)
+
+
+REF_PY = "/root/reference/GNNAdvisor"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_PY), reason="the reference tree is only mounted in the authoring container")
+def test_dataset_equals_the_reference_loader_run_live(tmp_path, monkeypatch):
+    """The reference's dataset.py, imported UNCHANGED (compat/ provides dgl and rabbit; `.cuda()` made a no-op because this
+    container has no GPU), builds its custom_dataset from the same .txt and .npz files: every field the training script
+    reads must be equal -- sizes, statistics, CSR, degrees, masks -- before and after rabbit_reorder()."""
+    import importlib
+    import os
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnnadvisor_osdi21_b200", "compat")
+    rng = np.random.default_rng(21)
+    n, e = 400, 6000
+    c = rng.integers(0, n // 20, e)                              # 20 communities of 20, most edges inside: reordering has work to do
+    src = c * 20 + rng.integers(0, 20, e)
+    dst = np.where(rng.random(e) < 0.8, c * 20 + rng.integers(0, 20, e), rng.integers(0, n, e))
+    shuffle = rng.permutation(n)
+    src, dst = shuffle[src], shuffle[dst]
+    src[0], dst[0] = n - 1, 0                                    # the largest id occurs: num_nodes = n in both formats
+    txt, npz = str(tmp_path / "g.txt"), str(tmp_path / "g.npz")
+    with open(txt, "w") as f:
+        f.write("".join("%d %d\n" % (a, b) for a, b in zip(src, dst)))
+    graph.save_npz(npz, src, dst, n)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    names = ("dataset", "dgl", "rabbit", "GNNAdvisor")
+    saved = {k: sys.modules.pop(k) for k in names if k in sys.modules}
+    sys.path[:0] = [compat, REF_PY]
+    try:
+        ref_mod = importlib.import_module("dataset")
+        assert ref_mod.__file__.startswith(REF_PY)
+        for path, from_txt in ((txt, True), (npz, False)):
+            ref = ref_mod.custom_dataset(path, 16, 5, load_from_txt=from_txt, verbose=False)
+            ours = graph.custom_dataset(path, 16, 5, load_from_txt=from_txt, verbose=False, device="cpu")
+
+            def same():
+                assert int(ref.num_nodes) == ours.num_nodes and ref.num_edges == ours.num_edges
+                assert ref.num_features == ours.num_features and ref.num_classes == ours.num_classes
+                assert abs(ref.avg_degree - ours.avg_degree) < 1e-12 and abs(float(ref.avg_edgeSpan) - ours.avg_edgeSpan) < 1e-9
+                assert np.array_equal(np.asarray(ref.edge_index), np.asarray(ours.edge_index))
+                assert torch.equal(ref.row_pointers, ours.row_pointers) and torch.equal(ref.column_index, ours.column_index)
+                assert ref.row_pointers.dtype == ours.row_pointers.dtype == torch.int32
+                assert torch.equal(ref.degrees, ours.degrees)
+            same()
+            assert ref.x.shape == ours.x.shape and torch.equal(ref.y, ours.y)
+            for m in ("train_mask", "val_mask", "test_mask"):
+                assert torch.equal(getattr(ref, m), getattr(ours, m)), m
+            ref.rabbit_reorder(); ours.rabbit_reorder()          # flag not set: nothing happens
+            same()
+            ref.reorder_flag = ours.reorder_flag = True
+            ref.rabbit_reorder(); ours.rabbit_reorder()          # same permutation on both sides (deterministic reordering)
+            same()
+            assert float(ours.avg_edgeSpan) > 0 and not np.array_equal(np.asarray(ours.edge_index), np.stack([src, dst]))
+    finally:
+        del sys.path[:2]
+        for k in names:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
