@@ -227,3 +227,52 @@ def test_same_seed_gives_the_reference_layers_initial_weights():
         for n in ("GNNAdvisor", "gnn_conv"):
             sys.modules.pop(n, None)
         sys.modules.update(saved)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_PY), reason="the reference tree is only mounted in the authoring container")
+@pytest.mark.parametrize("model", ["gcn", "gin"])
+def test_models_equal_the_reference_layers_run_live(setup, model):
+    """The reference's gnn_conv.py (unchanged) and this package's layers.py, both on the same extension surface (the CPU
+    oracle), same seed: GNNA_main.py's two models give the same output, loss and weight gradients -- the layers call the
+    extension with the same operands in the same order.  (ScatterAndGather too.)"""
+    import importlib
+    import os
+    import sys
+    surface, info, _, _, n = setup
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnnadvisor_osdi21_b200", "compat")
+    saved = {k: sys.modules.pop(k) for k in ("GNNAdvisor", "gnn_conv") if k in sys.modules}
+    sys.path[:0] = [compat, REF_PY]
+    try:
+        ref = importlib.import_module("gnn_conv")
+        ref.GNNA = surface                                       # the reference's `import GNNAdvisor as GNNA`
+        dims = [12, 8, 4] if model == "gcn" else [12, 8, 8, 8, 8, 4]            # GNNA_main.py:142-171
+        x = torch.randn(n, 12, generator=torch.Generator().manual_seed(3)) * 0.1
+        y = torch.randint(0, 4, (n,), generator=torch.Generator().manual_seed(4))
+        results = []
+        for mod in (layers, ref):
+            torch.manual_seed(11)
+            conv = mod.GCNConv if model == "gcn" else mod.GINConv
+            convs = [conv(a, b) for a, b in zip(dims[:-1], dims[1:])]
+            h = x
+            for i, c in enumerate(convs):
+                h = c(h, info)
+                if i < len(convs) - 1:
+                    h = torch.relu(h)
+            loss = torch.nn.functional.nll_loss(torch.log_softmax(h, dim=1), y)
+            loss.backward()
+            results.append((h.detach(), float(loss), [c.weights.grad.clone() for c in convs]))
+        (h_a, l_a, g_a), (h_b, l_b, g_b) = results
+        assert torch.equal(h_a, h_b) and l_a == l_b
+        for a, b in zip(g_a, g_b):
+            assert torch.equal(a, b)
+        # ScatterAndGather: forward only -- the reference's backward returns ONE gradient for two inputs (gnn_conv.py:21-28),
+        # which autograd rejects ("incorrect number of gradients"); ours returns (d_input, None)
+        xs = torch.randn(n, 6)
+        assert torch.equal(layers.ScatterAndGather.apply(xs, info), ref.ScatterAndGather.apply(xs, info))
+        with pytest.raises(RuntimeError, match="incorrect number of gradients"):
+            ref.ScatterAndGather.apply(xs.clone().requires_grad_(True), info).sum().backward()
+    finally:
+        del sys.path[:2]
+        for k in ("GNNAdvisor", "gnn_conv"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
