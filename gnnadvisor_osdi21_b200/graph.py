@@ -306,6 +306,12 @@ class GraphDataset(torch.nn.Module):
         self.x = torch.randn(self.num_nodes, self.num_features, generator=gen).to(self.device)      # dataset.py:129
         self.y = torch.ones(self.num_nodes, dtype=torch.long, device=self.device)                   # dataset.py:136
 
+    @property
+    def val(self):
+        """The edge values the reference keeps as a Python list `[1] * num_edges` (dataset.py:106) and hands to
+        unitest.Verification.reference (GNNA_main.py:122); a float32 array of ones serves the same callers."""
+        return np.ones(self.num_edges, dtype=np.float32)
+
     def _refresh_degrees(self):
         self.degrees = degrees_from_row_ptr_host(self.row_pointers).to(self.device)
 

@@ -50,3 +50,70 @@ def test_flag_table_is_the_reference_script_verbatim():
     assert len(ref) == 17
     for dest, typ, default, choices in REFERENCE_FLAGS:
         assert ref[dest] == (typ.__name__, str(default), choices), dest
+
+
+REF_PY = "/root/reference/GNNAdvisor"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PY), reason="the reference tree is only mounted in the authoring container")
+def test_verification_of_the_reference_run_live_agrees_with_ours(tmp_path, monkeypatch, capsys):
+    """GNNA_main.py:116-125 / unitest.py:33-63: SAG on all-ones features against a CPU sparse product of the RAW edge list,
+    PASSED when all but 1e-4 of the elements are EXACTLY equal.  The reference's Verification class, imported unchanged, and
+    main.verify_spmm judge the same dataset object (ours) through the same extension surface (the CPU oracle here; compat/
+    provides torch_sparse): both print PASSED for a correct aggregation and FAILED for a broken one."""
+    import importlib
+    import sys
+    import numpy as np
+    import torch
+    import oracle
+    from gnnadvisor_osdi21_b200 import graph, ops
+    rng = np.random.default_rng(3)
+    n, e = 300, 5000
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    keep = src != dst
+    src, dst = np.concatenate([src[keep], dst[keep]]), np.concatenate([dst[keep], src[keep]])
+    key = np.unique(src * n + dst)                           # the datasets of the reference hold every edge once
+    src, dst = key // n, key % n
+    npz = str(tmp_path / "g.npz")
+    graph.save_npz(npz, src, dst, n)
+    ds = graph.custom_dataset(npz, 16, 4, load_from_txt=False, device="cpu")
+    pp, pn = (t.int() for t in ops.build_part(8, ds.row_pointers))
+
+    class Info:
+        pass
+    info = Info()
+    info.row_pointers, info.column_index, info.degrees = ds.row_pointers, ds.column_index, ds.degrees
+    info.partPtr, info.part2Node, info.partSize, info.dimWorker, info.warpPerBlock = pp, pn, 8, 16, 4
+    broken = {"on": False}
+
+    def sag(X, rp, ci, deg, ppt, pnt, ps, dw, wpb):
+        out = torch.from_numpy(oracle.SAG(X.numpy(), rp.numpy(), ci.numpy(), None, ppt.numpy(), pnt.numpy()))
+        if broken["on"]:
+            out[::7] += 1.0
+        return out
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(ops, "SAG", sag)
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnnadvisor_osdi21_b200", "compat")
+    saved = {k: sys.modules.pop(k) for k in ("GNNAdvisor", "unitest", "torch_sparse") if k in sys.modules}
+    sys.path[:0] = [compat, REF_PY]
+    try:
+        unitest = importlib.import_module("unitest")
+        assert unitest.__file__.startswith(REF_PY)
+        unitest.GNNA.SAG = sag
+        for state, verdict in ((False, "PASSED"), (True, "FAILED")):
+            broken["on"] = state
+            capsys.readouterr()
+            v = unitest.Verification(16, info.row_pointers, info.column_index, info.degrees, info.partPtr, info.part2Node, 8, 16, 4)
+            v.compute()
+            v.reference(ds.edge_index, ds.val, ds.num_nodes)
+            v.compare()
+            theirs = capsys.readouterr().out
+            ok = main.verify_spmm(info, ds, 16)
+            mine = capsys.readouterr().out
+            assert ("# Verification " + verdict) in theirs and ("# Verification " + verdict) in mine and ok == (verdict == "PASSED")
+            assert theirs.splitlines() == mine.splitlines()                  # the same three lines, in the same order
+    finally:
+        del sys.path[:2]
+        for k in ("GNNAdvisor", "unitest", "torch_sparse"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)

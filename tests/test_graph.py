@@ -249,6 +249,7 @@ def test_dataset_equals_the_reference_loader_run_live(tmp_path, monkeypatch):
                 assert ref.row_pointers.dtype == ours.row_pointers.dtype == torch.int32
                 assert torch.equal(ref.degrees, ours.degrees)
             same()
+            assert len(ref.val) == len(ours.val) == e and set(ref.val) == {1} and bool((ours.val == 1).all())
             assert ref.x.shape == ours.x.shape and torch.equal(ref.y, ours.y)
             for m in ("train_mask", "val_mask", "test_mask"):
                 assert torch.equal(getattr(ref, m), getattr(ours, m)), m
