@@ -1,6 +1,6 @@
-"""Host side of the dataset path: the reference's loader as written (GNNAdvisor/dataset.py:62-72 text
-loop, :108-111 scipy coo -> csr from Python lists, :120-122 degree list) against libgnna_b200.so's (csrc/dataset.cu), on the
-same files.  CPU only -- runs in the authoring container.
+"""Host side of the dataset path: the reference's own loader, imported unchanged (GNNAdvisor/dataset.py:
+:62-72 text loop, :108-111 scipy coo -> csr from Python lists, :120-122 degree list) against libgnna_b200.so's
+(csrc/dataset.cu), on the same files.  CPU only -- runs in the authoring container, where /root/reference is mounted.
 
     OMP_WAIT_POLICY=passive python tools/dataset_path.py [edges ...]      > profiles/r02_dataset_path_cpu.txt
 """
@@ -10,7 +10,6 @@ import tempfile
 import time
 
 import numpy as np
-import scipy.sparse as sp
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,28 +17,31 @@ from gnnadvisor_osdi21_b200 import graph  # noqa: E402
 
 
 def reference_loader(path):
-    """dataset.py:58-122 as written (minus dgl and .cuda())."""
+    """The reference's own loader, imported UNCHANGED from /root/reference (compat/ provides dgl and rabbit, `.cuda()` is
+    made a no-op: no GPU here) and timed by its own verbose phase timers (dataset.py:74-79 loading, :109-115 CSR build);
+    the degree list (:120-122) is what is left of init_edges."""
+    import contextlib
+    import importlib
+    import io
+    import re
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnnadvisor_osdi21_b200", "compat")
+    sys.path[:0] = [compat, "/root/reference/GNNAdvisor"]
+    try:
+        ref = importlib.import_module("dataset")
+    finally:
+        del sys.path[:2]
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    obj = ref.custom_dataset.__new__(ref.custom_dataset)
+    torch.nn.Module.__init__(obj)
+    obj.nodes, obj.load_from_txt, obj.verbose_flag = set(), True, True
+    text = io.StringIO()
     t0 = time.perf_counter()
-    nodes, src_li, dst_li = set(), [], []
-    with open(path, "r") as fp:
-        for line in fp:
-            src, dst = line.strip('\n').split()
-            src, dst = int(src), int(dst)
-            src_li.append(src)
-            dst_li.append(dst)
-            nodes.add(src)
-            nodes.add(dst)
-    num_edges, num_nodes = len(src_li), max(nodes) + 1
-    edge_index = np.stack([src_li, dst_li])
-    t1 = time.perf_counter()
-    val = [1] * num_edges
-    csr = sp.coo_matrix((val, edge_index), shape=(num_nodes, num_nodes)).tocsr()
-    column_index, row_pointers = torch.IntTensor(csr.indices), torch.IntTensor(csr.indptr)
-    t2 = time.perf_counter()
-    degrees = (row_pointers[1:] - row_pointers[:-1]).tolist()
-    deg = torch.sqrt(torch.FloatTensor(list(map(lambda x: x if x > 0 else 1, degrees))))
-    t3 = time.perf_counter()
-    return (row_pointers, column_index, deg), (t1 - t0, t2 - t1, t3 - t2)
+    with contextlib.redirect_stdout(text):
+        obj.init_edges(path)
+    total = time.perf_counter() - t0
+    load = float(re.search(r"# Loading \(txt\) ([0-9.]+)s", text.getvalue()).group(1))
+    csr = float(re.search(r"# Build CSR after reordering \(s\): ([0-9.]+)", text.getvalue()).group(1))
+    return (obj.row_pointers, obj.column_index, obj.degrees), (load, csr, total - load - csr)
 
 
 def native_loader(path):
@@ -74,9 +76,11 @@ def main():
         same = torch.equal(rp, rrp) and torch.equal(ci, rci) and torch.equal(deg, rdeg)
         print("\n%d edge lines, %d nodes, %.0f MB of text -> CSR with %d edges; native result == reference result: %s"
               % (len(s), rp.numel() - 1, mb, ci.numel(), same))
-        for name, a, b in zip(("parse text", "coo -> csr", "degrees"), tr, tn):
+        for name, a, b in zip(("parse text", "coo -> csr", "rest*"), tr, tn):
             print("  %-12s reference %8.3f s   native %7.3f s   %6.1fx" % (name, a, b, a / max(b, 1e-9)))
         print("  %-12s reference %8.3f s   native %7.3f s   %6.1fx" % ("total", sum(tr), sum(tn), sum(tr) / sum(tn)))
+        print("  (* reference: everything else in init_edges -- np.stack of the two lists, edge-span statistics, the [1]*E list, the degree map;"
+              " native: the degree vector)")
         assert same
 
 
